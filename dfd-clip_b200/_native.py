@@ -1,0 +1,222 @@
+"""ctypes binding of libdfdclip_b200.so — the C ABI declared in include/dfdclip_b200.h.
+
+There is no Python/CPU fallback: if the shared library is missing or a call fails, this module raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdfdclip_b200.so")
+
+c_void_p, c_int, c_int64, c_size_t, c_float = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float)
+
+EPI_STORE_BF16, EPI_STORE_BF16_QGELU, EPI_STORE_F32, EPI_ADD_F32 = 0, 1, 2, 3
+
+# Every symbol include/dfdclip_b200.h declares (tests check the library exports each of them).
+EXPORTS = (
+    "dfd_version", "dfd_last_error", "dfd_ctx_create", "dfd_ctx_destroy",
+    "dfd_gemm_bf16", "dfd_layernorm", "dfd_patchify", "dfd_mha_fwd",
+    "dfd_encoder_packed_bytes", "dfd_encoder_workspace_bytes", "dfd_encoder_pack_weights", "dfd_encoder_forward",
+    "dfd_decoder_workspace_bytes", "dfd_decoder_forward", "dfd_project_logits", "dfd_decoder_attention",
+)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class VitDims(ctypes.Structure):
+    _fields_ = [("image_size", c_int), ("patch_size", c_int), ("width", c_int), ("heads", c_int), ("layers", c_int)]
+
+
+_PP = ctypes.POINTER(c_void_p)
+
+
+class VitWeights(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "conv1_weight", "class_embedding", "positional_embedding", "ln_pre_weight", "ln_pre_bias")] + [
+        (n, _PP) for n in (
+            "ln_1_weight", "ln_1_bias", "in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias",
+            "ln_2_weight", "ln_2_bias", "c_fc_weight", "c_fc_bias", "c_proj_weight", "c_proj_bias")]
+
+
+class DecoderWeights(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "class_embedding", "positional_embedding", "ln_pre_weight", "ln_pre_bias", "ln_post_weight",
+        "ln_post_bias")] + [
+        (n, _PP) for n in (
+            "ln_1_weight", "ln_1_bias", "in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias",
+            "ln_2_weight", "ln_2_bias", "c_fc_weight", "c_fc_bias", "c_proj_weight", "c_proj_bias")]
+
+
+class KvTaps(ctypes.Structure):
+    _fields_ = [("k", _PP), ("v", _PP), ("stride_b", c_int64), ("stride_t", c_int64), ("stride_p", c_int64)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+_ctxs = {}
+
+
+def load_library():
+    """dlopen the in-tree library; raise (never fall back) when it is absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                "libdfdclip_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python dfd-clip_b200/build.py`. There is no CPU/PyTorch fallback for this path." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.dfd_last_error.restype = ctypes.c_char_p
+        lib.dfd_version.restype = c_int
+        lib.dfd_ctx_create.argtypes = [c_int, ctypes.POINTER(c_void_p)]
+        lib.dfd_ctx_destroy.argtypes = [c_void_p]
+        lib.dfd_gemm_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                      c_int, c_int, c_int, c_int, c_void_p]
+        lib.dfd_layernorm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int64, c_int, c_void_p]
+        lib.dfd_patchify.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+        lib.dfd_mha_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+        lib.dfd_encoder_packed_bytes.argtypes = [ctypes.POINTER(VitDims)]
+        lib.dfd_encoder_packed_bytes.restype = c_size_t
+        lib.dfd_encoder_workspace_bytes.argtypes = [ctypes.POINTER(VitDims), c_int]
+        lib.dfd_encoder_workspace_bytes.restype = c_size_t
+        lib.dfd_encoder_pack_weights.argtypes = [c_void_p, ctypes.POINTER(VitDims), ctypes.POINTER(VitWeights),
+                                                 c_void_p, c_void_p]
+        lib.dfd_encoder_forward.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p, c_int, c_int,
+                                            c_int, _PP, _PP, c_void_p, c_size_t, c_void_p]
+        lib.dfd_decoder_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        lib.dfd_decoder_workspace_bytes.restype = c_size_t
+        lib.dfd_decoder_forward.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
+                                            ctypes.POINTER(KvTaps), c_void_p, c_int, c_int, c_int, c_void_p,
+                                            c_void_p, c_void_p, c_size_t, c_void_p]
+        lib.dfd_project_logits.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
+                                           c_void_p]
+        lib.dfd_decoder_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                              c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                              c_size_t, c_void_p]
+        for name in EXPORTS:
+            fn = getattr(lib, name)
+            if fn.restype is c_int and name not in ("dfd_version",):
+                fn.restype = c_int
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().dfd_last_error()
+        raise NativeError("libdfdclip_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def ctx(device):
+    """Per-device context handle (created on first use)."""
+    lib = load_library()
+    if not torch.cuda.is_available():
+        raise NativeError("dfdclip_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    index = torch.device(device).index
+    if index is None:
+        index = torch.cuda.current_device()
+    with _lib_lock:
+        handle = _ctxs.get(index)
+    if handle is None:
+        out = c_void_p()
+        check(lib.dfd_ctx_create(index, ctypes.byref(out)))
+        handle = out
+        with _lib_lock:
+            _ctxs[index] = handle
+    return handle
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL for None)."""
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (keeps no reference: caller must keep the tensors alive)."""
+    arr = (c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = 0 if t is None else t.data_ptr()
+    return arr
+
+
+# ------------------------------------------------------------------------------------------ unit kernels
+def gemm_bf16(a, w, bias, out, epilogue):
+    """out (epilogue) a[M,K] @ w[N,K]^T on the tcgen05 kernel. a, w: bf16 2-D with unit inner stride."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    assert out.stride(1) == 1
+    m, k = a.shape
+    n = w.shape[0]
+    check(load_library().dfd_gemm_bf16(ctx(a.device), ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out),
+                                       out.stride(0), m, n, k, epilogue, stream_ptr(a.device)))
+    return out
+
+
+def layernorm(x, gamma, beta, pos=None, out_dtype=torch.bfloat16, out=None):
+    """Row LayerNorm of fp32 x [rows, D] (eps 1e-5); optional periodic `pos` [period, D] added first."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty((rows, d), dtype=out_dtype, device=x.device)
+    bf = out.dtype == torch.bfloat16
+    check(load_library().dfd_layernorm(ctx(x.device), ptr(x), ptr(gamma), ptr(beta), ptr(pos),
+                                       0 if pos is None else pos.shape[0], ptr(out) if bf else None,
+                                       None if bf else ptr(out), rows, d, stream_ptr(x.device)))
+    return out
+
+
+def patchify(frames, patch, kp=None):
+    """frames fp32 [F,3,R,R] -> bf16 [F*(P+1), Kp] patch matrix with zero cls rows."""
+    assert frames.dtype == torch.float32 and frames.is_contiguous() and frames.dim() == 4
+    f, _, r, _ = frames.shape
+    k = 3 * patch * patch
+    kp = kp or (k + 63) // 64 * 64
+    g = r // patch
+    out = torch.empty((f * (g * g + 1), kp), dtype=torch.bfloat16, device=frames.device)
+    check(load_library().dfd_patchify(ctx(frames.device), ptr(frames), ptr(out), f, r, patch, kp,
+                                      stream_ptr(frames.device)))
+    return out
+
+
+def mha_fwd(qkv, n_frames, seq, heads):
+    """Encoder self-attention on a packed bf16 QKV buffer [n_frames*seq, 3*heads*64] -> mix bf16 [.., heads*64]."""
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    mix = torch.empty((n_frames * seq, heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    check(load_library().dfd_mha_fwd(ctx(qkv.device), ptr(qkv), ptr(mix), n_frames, seq, heads,
+                                     stream_ptr(qkv.device)))
+    return mix
+
+
+def decoder_attention(qs, k, v, pos_emb, mask):
+    """qs fp32 [B,H,128]; k, v bf16 [B,T,P,H,64] (any b/t/p strides, unit inner strides); mask bool [B,T]."""
+    b, t, p, h, dh = k.shape
+    assert dh == 64 and k.stride(4) == 1 and k.stride(3) == 64 and k.stride() == v.stride()
+    assert k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
+    m8 = mask.to(torch.uint8).contiguous()
+    mix = torch.empty((b, h * 64), dtype=torch.float32, device=k.device)
+    ws = torch.empty((b * t * h * 130,), dtype=torch.float32, device=k.device)
+    check(load_library().dfd_decoder_attention(
+        ctx(k.device), ptr(qs.contiguous()), ptr(k), ptr(v), k.stride(0), k.stride(1), k.stride(2),
+        ptr(None if pos_emb is None else pos_emb.contiguous()), ptr(m8), b, t, p, h, ptr(mix), ptr(ws),
+        ws.numel() * 4, stream_ptr(k.device)))
+    return mix
+
+
+def project_logits(feature, proj, scale=5.0):
+    b, d = feature.shape
+    o = proj.shape[1]
+    out = torch.empty((b, o), dtype=torch.float32, device=feature.device)
+    check(load_library().dfd_project_logits(ctx(feature.device), ptr(feature.contiguous()), ptr(proj.contiguous()),
+                                            b, d, o, scale, ptr(out), stream_ptr(feature.device)))
+    return out

@@ -1,0 +1,83 @@
+"""Build libdfdclip_b200.so (sm_100a only) from csrc/*.cu with nvcc, in-tree.
+
+Used by __graft_entry__.build() and runnable by hand: `python dfd-clip_b200/build.py [--force]`.
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels to the GPU box.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB_PATH = os.path.join(HERE, "libdfdclip_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "-I", INCLUDE,
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for root in (CSRC, INCLUDE):
+        for f in sorted(os.listdir(root)):
+            if f.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(root, f), "rb") as fh:
+                    h.update(f.encode())
+                    h.update(fh.read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a and link the shared library. Returns its path."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    stamp = os.path.join(OBJ_DIR, "stamp.txt")
+    digest = _digest()
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
+        if verbose:
+            sys.stderr.write(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, _sources()))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    with open(stamp, "w") as fh:
+        fh.write(digest)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

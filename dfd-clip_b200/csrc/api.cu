@@ -1,0 +1,83 @@
+// C-ABI plumbing: version, thread-local error string, per-device context, TMA tensor-map construction.
+#include "host_common.h"
+
+#include <cudaTypedefs.h>
+
+namespace dfd {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void clear_error() { g_err[0] = 0; }
+
+int make_tmap_2d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                 uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  if (!ctx || !ctx->encode_tiled) return fail(DFD_ERR_INVALID, "tensor map: context has no driver entry point");
+  if (box_cols * elem_bytes != 128) return fail(DFD_ERR_INVALID, "tensor map: box inner extent must be 128 bytes");
+  if ((ld * elem_bytes) % 16 != 0) return fail(DFD_ERR_INVALID, "tensor map: row pitch must be a multiple of 16 bytes");
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail(DFD_ERR_INVALID, "tensor map: base must be 16-byte aligned");
+  auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ctx->encode_tiled);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DFD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)",
+                (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+  return 0;
+}
+
+}  // namespace dfd
+
+extern "C" {
+
+int dfd_version(void) { return DFD_ABI_VERSION; }
+
+const char* dfd_last_error(void) { return dfd::g_err; }
+
+int dfd_ctx_create(int device, dfd_ctx** out) {
+  dfd::clear_error();
+  if (!out) return dfd::fail(DFD_ERR_INVALID, "dfd_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  DFD_CUDA_OK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return dfd::fail(DFD_ERR_INVALID, "dfd_ctx_create: no such device %d", device);
+  cudaDeviceProp prop;
+  DFD_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return dfd::fail(DFD_ERR_UNSUPPORTED,
+                     "dfd_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only (no fallback)",
+                     device, prop.major, prop.minor);
+  DFD_CUDA_OK(cudaSetDevice(device));
+  DFD_CUDA_OK(cudaFree(0));  // make sure the primary context exists
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  DFD_CUDA_OK(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn)
+    return dfd::fail(DFD_ERR_CUDA, "dfd_ctx_create: cuTensorMapEncodeTiled not available from the driver");
+  dfd_ctx* c = new dfd_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  c->encode_tiled = fn;
+  *out = c;
+  return 0;
+}
+
+int dfd_ctx_destroy(dfd_ctx* ctx) {
+  dfd::clear_error();
+  delete ctx;
+  return 0;
+}
+
+}  // extern "C"

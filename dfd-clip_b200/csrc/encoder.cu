@@ -1,0 +1,242 @@
+// Encoder orchestration: VisionTransformer.forward / Transformer.forward / ResidualAttentionBlock.forward
+// (src/clip/model.py:276-294, 236-251, 220-226) as one C call that enqueues every kernel of the frame
+// encoder on the caller's stream.
+//
+// Data layout in HBM (M = n_frames * L rows, L = P + 1 tokens per frame, D = width):
+//   x      fp32 [M, D]     residual stream (updated in place by the TMA reduce-add GEMM epilogues)
+//   u      bf16 [M, D]     LayerNorm output = A operand of the QKV / c_fc GEMMs
+//   qkv_l  bf16 [M, 3D]    per layer, row = [q | k | v]; the decoder reads K/V taps from here in place
+//   mix    bf16 [M, D]     attention output = A operand of out_proj
+//   hid    bf16 [M, 4D]    QuickGELU(c_fc) = A operand of c_proj
+//   patches bf16 [M, Kp]   im2col of the frames (cls rows zero) = A operand of the patch-embedding GEMM
+#include "common.cuh"
+#include "host_common.h"
+
+namespace dfd {
+
+int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+              void* out, int64_t ldo, int M, int N, int K, int epilogue, cudaStream_t stream);
+int layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int pos_period, void* out_bf16,
+              float* out_f32, int64_t rows, int D, cudaStream_t stream);
+int patchify(const float* frames, void* out, int n_frames, int R, int patch, int Kp, cudaStream_t stream);
+int mha_fwd(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
+int cast_pad_bf16(const float* src, void* dst, int64_t rows, int cols, int dst_ld, cudaStream_t stream);
+
+static inline size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct VitShape {
+  int R, p, D, H, layers, G, P, L, K, Kp;
+};
+
+static int vit_shape(const dfd_vit_dims* d, VitShape* s) {
+  DFD_CHECK_ARG(d != nullptr, "encoder: dims is NULL");
+  s->R = d->image_size; s->p = d->patch_size; s->D = d->width; s->H = d->heads; s->layers = d->layers;
+  DFD_CHECK_ARG(s->R > 0 && s->p > 0 && s->D > 0 && s->H > 0 && s->layers > 0, "encoder: non-positive dimension");
+  DFD_CHECK_ARG(s->R % s->p == 0, "encoder: image size %d is not a multiple of the patch size %d", s->R, s->p);
+  DFD_CHECK_ARG(s->D == 64 * s->H, "encoder: width %d != 64 * heads %d (head dim must be 64)", s->D, s->H);
+  DFD_CHECK_ARG(s->D % 256 == 0, "encoder: width %d must be a multiple of 256", s->D);
+  s->G = s->R / s->p;
+  s->P = s->G * s->G;
+  s->L = s->P + 1;
+  s->K = 3 * s->p * s->p;
+  s->Kp = (s->K + 63) & ~63;
+  DFD_CHECK_ARG(s->L <= 272, "encoder: %d tokens per frame exceed the attention kernel's limit of 272", s->L);
+  return 0;
+}
+
+// Packed parameter block. Offsets in bytes from the start; bf16 matrices first, fp32 vectors after.
+struct PackedLayout {
+  size_t conv_w;            // bf16 [D, Kp]
+  size_t posc;              // fp32 [L, D]: row 0 = class_embedding + pos[0], row l = pos[l]
+  size_t ln_pre_w, ln_pre_b;
+  size_t layer0, layer_stride;
+  // within a layer
+  size_t w_in, w_out, w_fc, w_proj;  // bf16
+  size_t b_in, b_out, b_fc, b_proj, ln1_w, ln1_b, ln2_w, ln2_b;  // fp32
+  size_t total;
+};
+
+static PackedLayout packed_layout(const VitShape& s) {
+  PackedLayout p{};
+  const size_t D = s.D;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += up256(bytes); return r; };
+  p.conv_w = take(D * s.Kp * 2);
+  p.posc = take(static_cast<size_t>(s.L) * D * 4);
+  p.ln_pre_w = take(D * 4);
+  p.ln_pre_b = take(D * 4);
+  p.layer0 = off;
+  size_t lo = 0;
+  auto ltake = [&](size_t bytes) { size_t r = lo; lo += up256(bytes); return r; };
+  p.w_in = ltake(3 * D * D * 2);
+  p.w_out = ltake(D * D * 2);
+  p.w_fc = ltake(4 * D * D * 2);
+  p.w_proj = ltake(4 * D * D * 2);
+  p.b_in = ltake(3 * D * 4);
+  p.b_out = ltake(D * 4);
+  p.b_fc = ltake(4 * D * 4);
+  p.b_proj = ltake(D * 4);
+  p.ln1_w = ltake(D * 4);
+  p.ln1_b = ltake(D * 4);
+  p.ln2_w = ltake(D * 4);
+  p.ln2_b = ltake(D * 4);
+  p.layer_stride = lo;
+  p.total = p.layer0 + p.layer_stride * s.layers;
+  return p;
+}
+
+struct EncWs {
+  size_t x, u, mix, hid, qkv, patches, total;
+};
+
+static EncWs enc_ws(const VitShape& s, int n_frames) {
+  EncWs w{};
+  const size_t M = static_cast<size_t>(n_frames) * s.L, D = s.D;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += up256(bytes); return r; };
+  w.x = take(M * D * 4);
+  w.u = take(M * D * 2);
+  w.mix = take(M * D * 2);
+  w.hid = take(M * 4 * D * 2);   // also hosts the patch matrix before layer 0 (Kp <= 4D)
+  w.qkv = take(M * 3 * D * 2);   // scratch QKV for layers whose taps are not requested
+  w.patches = w.hid;
+  w.total = off;
+  return w;
+}
+
+__global__ void build_posc_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ posc,
+                                  int L, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L * D) posc[i] = pos[i] + (i < D ? cls[i] : 0.f);
+}
+
+int encoder_pack_weights(const dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd_vit_weights* w, void* packed,
+                         cudaStream_t stream) {
+  VitShape s;
+  DFD_TRY(vit_shape(dims, &s));
+  DFD_CHECK_ARG(w && packed, "encoder_pack_weights: null pointer");
+  DFD_CHECK_ARG(s.Kp <= 4 * s.D, "encoder_pack_weights: patch vector longer than the MLP hidden size");
+  const PackedLayout pl = packed_layout(s);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  const size_t D = s.D;
+  auto copy_f32 = [&](size_t off, const float* src, size_t n) -> int {
+    DFD_CHECK_ARG(src != nullptr, "encoder_pack_weights: missing parameter tensor");
+    DFD_CUDA_OK(cudaMemcpyAsync(base + off, src, n * 4, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  };
+  DFD_CHECK_ARG(w->conv1_weight && w->class_embedding && w->positional_embedding, "encoder_pack_weights: missing stem");
+  DFD_TRY(cast_pad_bf16(w->conv1_weight, base + pl.conv_w, s.D, s.K, s.Kp, stream));
+  build_posc_kernel<<<(s.L * s.D + 255) / 256, 256, 0, stream>>>(w->class_embedding, w->positional_embedding,
+                                                               reinterpret_cast<float*>(base + pl.posc), s.L, s.D);
+  DFD_CUDA_OK(cudaGetLastError());
+  DFD_TRY(copy_f32(pl.ln_pre_w, w->ln_pre_weight, D));
+  DFD_TRY(copy_f32(pl.ln_pre_b, w->ln_pre_bias, D));
+  for (int l = 0; l < s.layers; ++l) {
+    const size_t lb = pl.layer0 + pl.layer_stride * l;
+    DFD_CHECK_ARG(w->in_proj_weight[l] && w->out_proj_weight[l] && w->c_fc_weight[l] && w->c_proj_weight[l],
+                  "encoder_pack_weights: missing weight of layer %d", l);
+    DFD_TRY(cast_pad_bf16(w->in_proj_weight[l], base + lb + pl.w_in, 3 * D, s.D, s.D, stream));
+    DFD_TRY(cast_pad_bf16(w->out_proj_weight[l], base + lb + pl.w_out, D, s.D, s.D, stream));
+    DFD_TRY(cast_pad_bf16(w->c_fc_weight[l], base + lb + pl.w_fc, 4 * D, s.D, s.D, stream));
+    DFD_TRY(cast_pad_bf16(w->c_proj_weight[l], base + lb + pl.w_proj, D, 4 * s.D, 4 * s.D, stream));
+    DFD_TRY(copy_f32(lb + pl.b_in, w->in_proj_bias[l], 3 * D));
+    DFD_TRY(copy_f32(lb + pl.b_out, w->out_proj_bias[l], D));
+    DFD_TRY(copy_f32(lb + pl.b_fc, w->c_fc_bias[l], 4 * D));
+    DFD_TRY(copy_f32(lb + pl.b_proj, w->c_proj_bias[l], D));
+    DFD_TRY(copy_f32(lb + pl.ln1_w, w->ln_1_weight[l], D));
+    DFD_TRY(copy_f32(lb + pl.ln1_b, w->ln_1_bias[l], D));
+    DFD_TRY(copy_f32(lb + pl.ln2_w, w->ln_2_weight[l], D));
+    DFD_TRY(copy_f32(lb + pl.ln2_b, w->ln_2_bias[l], D));
+  }
+  (void)ctx;
+  return 0;
+}
+
+int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const float* frames, int n_frames,
+                    int num_run_layers, int last_qkv_only, void* const* qkv_out, float* const* x_out, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream) {
+  VitShape s;
+  DFD_TRY(vit_shape(dims, &s));
+  DFD_CHECK_ARG(packed && frames, "encoder_forward: null pointer");
+  DFD_CHECK_ARG(n_frames >= 0, "encoder_forward: negative frame count");
+  DFD_CHECK_ARG(num_run_layers >= 0 && num_run_layers <= s.layers, "encoder_forward: num_run_layers=%d out of range",
+                num_run_layers);
+  if (n_frames == 0) return 0;
+  const int64_t M64 = static_cast<int64_t>(n_frames) * s.L;
+  DFD_CHECK_ARG(M64 < (1ll << 31) - 256, "encoder_forward: too many frames for one call (%d)", n_frames);
+  const int M = static_cast<int>(M64);
+  const EncWs wl = enc_ws(s, n_frames);
+  if (!workspace || workspace_bytes < wl.total)
+    return fail(DFD_ERR_WORKSPACE, "encoder_forward: workspace %zu < %zu bytes", workspace_bytes, wl.total);
+  const PackedLayout pl = packed_layout(s);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(ws + wl.x);
+  void* u = ws + wl.u;
+  void* mix = ws + wl.mix;
+  void* hid = ws + wl.hid;
+  void* patches = ws + wl.patches;
+  const int D = s.D;
+  auto f32p = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+
+  // stem: conv1 as a GEMM over the patch matrix (cls rows are zero rows), then cls/pos add fused into ln_pre
+  DFD_TRY(patchify(frames, patches, n_frames, s.R, s.p, s.Kp, stream));
+  DFD_TRY(gemm_bf16(ctx, patches, s.Kp, pk + pl.conv_w, s.Kp, nullptr, x, D, M, D, s.Kp, DFD_EPI_STORE_F32, stream));
+  DFD_TRY(layernorm(x, f32p(pl.ln_pre_w), f32p(pl.ln_pre_b), f32p(pl.posc), s.L, nullptr, x, M, D, stream));
+
+  for (int l = 0; l < num_run_layers; ++l) {
+    const size_t lb = pl.layer0 + pl.layer_stride * l;
+    void* qkv = (qkv_out && qkv_out[l]) ? qkv_out[l] : static_cast<void*>(ws + wl.qkv);
+    // a = attn(ln_1(x))
+    DFD_TRY(layernorm(x, f32p(lb + pl.ln1_w), f32p(lb + pl.ln1_b), nullptr, 0, u, nullptr, M, D, stream));
+    DFD_TRY(gemm_bf16(ctx, u, D, pk + lb + pl.w_in, D, f32p(lb + pl.b_in), qkv, 3 * D, M, 3 * D, D, DFD_EPI_STORE_BF16,
+                      stream));
+    if (l == num_run_layers - 1 && last_qkv_only) break;
+    DFD_TRY(mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
+    // x = x + out_proj(mix)
+    DFD_TRY(gemm_bf16(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D, DFD_EPI_ADD_F32, stream));
+    // x = x + c_proj(quickgelu(c_fc(ln_2(x))))
+    DFD_TRY(layernorm(x, f32p(lb + pl.ln2_w), f32p(lb + pl.ln2_b), nullptr, 0, u, nullptr, M, D, stream));
+    DFD_TRY(gemm_bf16(ctx, u, D, pk + lb + pl.w_fc, D, f32p(lb + pl.b_fc), hid, 4 * D, M, 4 * D, D,
+                      DFD_EPI_STORE_BF16_QGELU, stream));
+    DFD_TRY(gemm_bf16(ctx, hid, 4 * D, pk + lb + pl.w_proj, 4 * D, f32p(lb + pl.b_proj), x, D, M, D, 4 * D,
+                      DFD_EPI_ADD_F32, stream));
+    if (x_out && x_out[l])
+      DFD_CUDA_OK(cudaMemcpyAsync(x_out[l], x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  return 0;
+}
+
+}  // namespace dfd
+
+extern "C" {
+
+size_t dfd_encoder_packed_bytes(const dfd_vit_dims* dims) {
+  dfd::VitShape s;
+  if (dfd::vit_shape(dims, &s) != 0) return 0;
+  return dfd::packed_layout(s).total;
+}
+
+size_t dfd_encoder_workspace_bytes(const dfd_vit_dims* dims, int n_frames) {
+  dfd::VitShape s;
+  if (n_frames <= 0 || dfd::vit_shape(dims, &s) != 0) return 0;
+  return dfd::enc_ws(s, n_frames).total;
+}
+
+int dfd_encoder_pack_weights(dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd_vit_weights* w, void* packed,
+                             void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_encoder_pack_weights: ctx is NULL");
+  return dfd::encoder_pack_weights(ctx, dims, w, packed, static_cast<cudaStream_t>(stream));
+}
+
+int dfd_encoder_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const float* frames, int n_frames,
+                        int num_run_layers, int last_qkv_only, void* const* qkv_out, float* const* x_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_encoder_forward: ctx is NULL");
+  return dfd::encoder_forward(ctx, dims, packed, frames, n_frames, num_run_layers, last_qkv_only, qkv_out, x_out,
+                              workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+// tcgen05 GEMM for the encoder's dense contractions (patch embedding, QKV, out-proj, MLP):
+//   out (epilogue) A[M,K] * W[N,K]^T,  bf16 operands, fp32 accumulation in TMEM.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: A and W tiles -> 4-stage smem ring (128-byte swizzle), mbarrier expect_tx
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) on the smem descriptors,
+//               tcgen05.commit releases smem stages and publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (thread = row), bias / QuickGELU, stage the tile in
+//               swizzled smem and write it with TMA (store, or reduce-add for the in-place residual)
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
+// tile i+1.
+//
+// Reference ops replaced: F.linear / nn.Linear / nn.Conv2d in src/clip/model.py:186,197,209,211,277.
+#include "common.cuh"
+#include "host_common.h"
+
+namespace dfd {
+
+namespace gemm {
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE = BM * BK * 2;           // 16 KB
+constexpr int B_STAGE = BN * BK * 2;           // 32 KB
+constexpr int OUT_BUF = 32 * 128;              // one epilogue staging box: 32 rows x 128 B
+constexpr int OUT_BUFS_PER_WARP = 2;
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
+constexpr int OFF_OUT = OFF_B + STAGES * B_STAGE;
+constexpr int OFF_BAR = OFF_OUT + EPI_WARPS * OUT_BUFS_PER_WARP * OUT_BUF;
+constexpr int NUM_BARS = 2 * STAGES + 4;
+constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;  // + slack for manual 1024 B alignment
+constexpr uint32_t TMEM_COLS = 512;
+}  // namespace gemm
+
+template <int EPI>
+__global__ void __launch_bounds__(gemm::THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+  using namespace gemm;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full[a], 1);
+        mbar_init(&tmem_empty[a], EPI_WARPS * 32);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
+          tma_load_2d(&tmA, &full_bar[stage], smem + OFF_A + stage * A_STAGE, kb * BK, m_blk * BM, kEvictNormal);
+          tma_load_2d(&tmB, &full_bar[stage], smem + OFF_B + stage * B_STAGE, kb * BK, n_blk * BN, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem + OFF_A + stage * A_STAGE);
+          const uint64_t b_desc = umma_desc_sw128(smem + OFF_B + stage * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance both descriptors by k*32 bytes inside the 128-byte swizzle atom
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
+    const int ew = warp - 2;
+    uint8_t* obuf = smem + OFF_OUT + ew * (OUT_BUFS_PER_WARP * OUT_BUF);
+    constexpr bool kOutF32 = (EPI == DFD_EPI_STORE_F32 || EPI == DFD_EPI_ADD_F32);
+    constexpr int COLS_PER_BOX = kOutF32 ? 32 : 64;
+    constexpr int NUM_BOX = BN / COLS_PER_BOX;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row0 = m_blk * BM + q * 32;
+      const int col0 = n_blk * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int box = 0; box < NUM_BOX; ++box) {
+        const int c = col0 + box * COLS_PER_BOX;
+        uint32_t packed[32];  // 128 bytes of output for this thread's row
+        if constexpr (kOutF32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + box * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c + j)) : make_float4(0, 0, 0, 0);
+            packed[j + 0] = __float_as_uint(__uint_as_float(r[j + 0]) + b4.x);
+            packed[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
+            packed[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
+            packed[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld32(t_row + box * 64 + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 =
+                  bias ? __ldg(reinterpret_cast<const float4*>(bias + c + half * 32 + j)) : make_float4(0, 0, 0, 0);
+              float v0 = __uint_as_float(r[j + 0]) + b4.x;
+              float v1 = __uint_as_float(r[j + 1]) + b4.y;
+              float v2 = __uint_as_float(r[j + 2]) + b4.z;
+              float v3 = __uint_as_float(r[j + 3]) + b4.w;
+              if constexpr (EPI == DFD_EPI_STORE_BF16_QGELU) {
+                v0 = quick_gelu_fast(v0);
+                v1 = quick_gelu_fast(v1);
+                v2 = quick_gelu_fast(v2);
+                v3 = quick_gelu_fast(v3);
+              }
+              packed[half * 16 + j / 2 + 0] = pack_bf16(v0, v1);
+              packed[half * 16 + j / 2 + 1] = pack_bf16(v2, v3);
+            }
+          }
+        }
+        if (box == NUM_BOX - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        // staging buffer `buf` was last read by the TMA store issued two boxes ago
+        if (lane == 0) tma_store_wait_read<OUT_BUFS_PER_WARP - 1>();
+        __syncwarp();
+        uint8_t* dst = obuf + buf * OUT_BUF + lane * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          // 128-byte swizzle: 16-byte chunk index XOR (row & 7); box base is 1024-byte aligned
+          uint4 v = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(dst + ((ch ^ (lane & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          if constexpr (EPI == DFD_EPI_ADD_F32)
+            tma_reduce_add_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
+          else
+            tma_store_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
+        }
+        if (lane == 0) tma_store_commit();
+        buf ^= 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// --------------------------------------------------------------------------------------------- host side
+template <int EPI>
+static int launch(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                  const float* bias, int M, int N, int K, cudaStream_t stream) {
+  using namespace gemm;
+  static bool configured[64] = {};
+  if (!configured[ctx->device & 63]) {
+    DFD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured[ctx->device & 63] = true;
+  }
+  const int num_tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;
+  gemm_bf16_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  DFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+              void* out, int64_t ldo, int M, int N, int K, int epilogue, cudaStream_t stream) {
+  using namespace gemm;
+  DFD_CHECK_ARG(ctx && A && W && out, "gemm: null pointer");
+  DFD_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  DFD_CHECK_ARG(N % BN == 0, "gemm: N=%d must be a multiple of %d", N, BN);
+  DFD_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte rows)");
+  DFD_CHECK_ARG(lda >= K && ldw >= K && ldo >= N, "gemm: leading dimension smaller than the row length");
+  const bool f32 = (epilogue == DFD_EPI_STORE_F32 || epilogue == DFD_EPI_ADD_F32);
+  DFD_CHECK_ARG(ldo % (f32 ? 4 : 8) == 0, "gemm: ldo must give 16-byte aligned rows");
+  DFD_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+                "gemm: operands must be 16-byte aligned");
+  DFD_CHECK_ARG(bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0, "gemm: bias must be 16-byte aligned");
+
+  CUtensorMap tmA, tmB, tmC;
+  DFD_TRY(make_tmap_2d(ctx, &tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK));
+  DFD_TRY(make_tmap_2d(ctx, &tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, BN, BK));
+  if (f32)
+    DFD_TRY(make_tmap_2d(ctx, &tmC, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldo, 32, 32));
+  else
+    DFD_TRY(make_tmap_2d(ctx, &tmC, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldo, 32, 64));
+
+  switch (epilogue) {
+    case DFD_EPI_STORE_BF16:
+      return launch<DFD_EPI_STORE_BF16>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+    case DFD_EPI_STORE_BF16_QGELU:
+      return launch<DFD_EPI_STORE_BF16_QGELU>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+    case DFD_EPI_STORE_F32:
+      return launch<DFD_EPI_STORE_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+    case DFD_EPI_ADD_F32:
+      return launch<DFD_EPI_ADD_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+    default:
+      return fail(DFD_ERR_INVALID, "gemm: unknown epilogue %d", epilogue);
+  }
+}
+
+}  // namespace dfd
+
+extern "C" int dfd_gemm_bf16(dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                             void* out, int64_t ldo, int M, int N, int K, int epilogue, void* stream) {
+  dfd::clear_error();
+  return dfd::gemm_bf16(ctx, A, lda, W, ldw, bias, out, ldo, M, N, K, epilogue, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,185 @@
+/*
+ * dfdclip_b200 — C ABI of the B200-native DFD-CLIP hot path (libdfdclip_b200.so).
+ *
+ * The reference (ODD2/DFD-CLIP) is pure Python and has no FFI for this path; the boundary the library
+ * sits under is the pair of Python surfaces
+ *     src/clip/model.py:276-294   VisionTransformer.forward  (frame encoder, per-layer q/k/v taps)
+ *     src/models.py:323-361       Decoder.forward            (temporal decoder / classification head)
+ *     src/models.py:498-566       Detector.predict           (encoder -> taps -> decoder -> 5*l/|l|)
+ * Every entry point below names the reference lines it replaces. All pointers are DEVICE pointers unless
+ * stated otherwise; the caller (PyTorch) owns every buffer; all work is enqueued asynchronously on the
+ * `stream` argument (a cudaStream_t passed as void*); nothing synchronises the device.
+ *
+ * Error convention: every function returns 0 on success or a DFD_ERR_* code; dfd_last_error() returns a
+ * thread-local message. There is no CPU fallback: unsupported shapes/configs are errors.
+ */
+#ifndef DFDCLIP_B200_H_
+#define DFDCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFD_ABI_VERSION 1
+
+enum {
+  DFD_OK = 0,
+  DFD_ERR_INVALID = 1,     /* bad argument / unsupported shape or config */
+  DFD_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed */
+  DFD_ERR_UNSUPPORTED = 3, /* device is not sm_100 */
+  DFD_ERR_WORKSPACE = 4    /* workspace too small */
+};
+
+/* GEMM epilogues (dfd_gemm_bf16). */
+enum {
+  DFD_EPI_STORE_BF16 = 0,       /* out_bf16 = acc + bias                     (QKV in_proj,  model.py:186)   */
+  DFD_EPI_STORE_BF16_QGELU = 1, /* out_bf16 = quickgelu(acc + bias)          (c_fc + QuickGELU, :166,:209)  */
+  DFD_EPI_STORE_F32 = 2,        /* out_f32  = acc + bias                     (conv1 as GEMM, :277)          */
+  DFD_EPI_ADD_F32 = 3           /* out_f32 += acc + bias  (in-place residual, out_proj/c_proj :222-223)     */
+};
+
+typedef struct dfd_ctx dfd_ctx;
+
+int dfd_version(void);
+const char* dfd_last_error(void);
+
+/* One context per device. Fails with DFD_ERR_UNSUPPORTED unless the device is compute capability 10.x. */
+int dfd_ctx_create(int device, dfd_ctx** out);
+int dfd_ctx_destroy(dfd_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Unit kernels (exported so each can be parity-tested on its own).
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* C[M,N] (epilogue) A[M,K] * W[N,K]^T. A, W: bf16, K contiguous, row pitches lda/ldw elements (multiples of 8).
+ * bias: fp32 [N] or NULL. out: bf16 or fp32 per `epilogue`, row pitch ldo elements. N % 256 == 0, K % 8 == 0.
+ * tcgen05 / TMEM / TMA kernel. Replaces F.linear / nn.Linear / nn.Conv2d of src/clip/model.py:186,197,209,211,277. */
+int dfd_gemm_bf16(dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
+                  int64_t ldo, int M, int N, int K, int epilogue, void* stream);
+
+/* Row LayerNorm, fp32 math, eps 1e-5, biased variance (src/clip/model.py:157-163).
+ * x fp32 [rows, D]; pos (optional) fp32 [pos_period, D] is added to row r as pos[r % pos_period] before the
+ * statistics (cls/positional embedding add of model.py:280-291 fused into ln_pre). Exactly one of
+ * out_bf16 / out_f32 is non-NULL; out_f32 may alias x. D must be a multiple of 128, <= 2048. */
+int dfd_layernorm(dfd_ctx* ctx, const float* x, const float* gamma, const float* beta, const float* pos,
+                  int pos_period, void* out_bf16, float* out_f32, int64_t rows, int D, void* stream);
+
+/* frames fp32 [n_frames,3,R,R] -> patch matrix bf16 [n_frames*(P+1), Kp]; row f*(P+1) is zero (cls slot),
+ * row f*(P+1)+1+p holds patch p flattened (c, i, j) like conv1.weight[D,3,p,p] (model.py:277-279).
+ * Columns [3*p*p, Kp) are zero. */
+int dfd_patchify(dfd_ctx* ctx, const float* frames, void* out_bf16, int n_frames, int R, int patch, int Kp,
+                 void* stream);
+
+/* Encoder self-attention over one packed QKV buffer (model.py:188-195): qkv bf16 [n_frames*L, 3*D]
+ * (row = [q | k | v], each H x 64), no mask, softmax over keys of (q/8).k; mix bf16 [n_frames*L, D]. dh = 64. */
+int dfd_mha_fwd(dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Encoder: VisionTransformer.forward (src/clip/model.py:276-294, Transformer.forward :236-251).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int image_size; /* R   */
+  int patch_size; /* p   */
+  int width;      /* D   */
+  int heads;      /* H, D == 64*H */
+  int layers;
+} dfd_vit_dims;
+
+/* fp32 device pointers in the reference state_dict layout. Per-layer members are HOST
+ * arrays of `layers` device pointers. */
+typedef struct {
+  const float* conv1_weight;         /* [D,3,p,p] */
+  const float* class_embedding;      /* [D]       */
+  const float* positional_embedding; /* [P+1,D]   */
+  const float* ln_pre_weight;
+  const float* ln_pre_bias;
+  const float* const* ln_1_weight;
+  const float* const* ln_1_bias;
+  const float* const* in_proj_weight; /* [3D,D] */
+  const float* const* in_proj_bias;   /* [3D]   */
+  const float* const* out_proj_weight; /* [D,D] */
+  const float* const* out_proj_bias;
+  const float* const* ln_2_weight;
+  const float* const* ln_2_bias;
+  const float* const* c_fc_weight;   /* [4D,D] */
+  const float* const* c_fc_bias;
+  const float* const* c_proj_weight; /* [D,4D] */
+  const float* const* c_proj_bias;
+} dfd_vit_weights;
+
+size_t dfd_encoder_packed_bytes(const dfd_vit_dims* dims);
+size_t dfd_encoder_workspace_bytes(const dfd_vit_dims* dims, int n_frames);
+
+/* Convert the fp32 parameters to the library's packed layout (bf16 GEMM operands, fp32 biases/LN/pos). */
+int dfd_encoder_pack_weights(dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd_vit_weights* w, void* packed,
+                             void* stream);
+
+/* frames fp32 [n_frames,3,R,R]. Runs layers [0, num_run_layers). If last_qkv_only != 0 the last of those
+ * layers stops after its QKV projection (its attention/MLP output is not needed: SURVEY note D1).
+ * qkv_out: HOST array [layers] of bf16 [n_frames*L, 3D] device buffers (NULL entry: QKV of that layer is kept
+ * only in scratch). x_out: NULL or HOST array [layers] of fp32 [n_frames*L, D] device buffers receiving the
+ * residual stream after each layer (`with_out`, model.py:242). */
+int dfd_encoder_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const float* frames,
+                        int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                        float* const* x_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Decoder: Decoder.forward / Transformer.forward / MultiheadAttention.forward (src/models.py:323-361,
+ * 259-269, 136-146) in fp32, streaming the tapped bf16 K/V once per block.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* class_embedding;      /* [D] */
+  const float* positional_embedding; /* [T,1,H,64] or NULL (op_mode.temporal_position == 0) */
+  const float* ln_pre_weight;
+  const float* ln_pre_bias;
+  const float* ln_post_weight;
+  const float* ln_post_bias;
+  /* HOST arrays of n_blocks device pointers */
+  const float* const* ln_1_weight;
+  const float* const* ln_1_bias;
+  const float* const* in_proj_weight; /* [2D,D] */
+  const float* const* in_proj_bias;   /* [2D]   */
+  const float* const* out_proj_weight; /* [D,D] */
+  const float* const* out_proj_bias;
+  const float* const* ln_2_weight;
+  const float* const* ln_2_bias;
+  const float* const* c_fc_weight;
+  const float* const* c_fc_bias;
+  const float* const* c_proj_weight;
+  const float* const* c_proj_bias;
+} dfd_decoder_weights;
+
+/* K/V of tapped layer i: element (b,t,p,h,c) lives at k[i] + b*stride_b + t*stride_t + p*stride_p + h*64 + c
+ * (bf16 elements). Views of the encoder's QKV buffers satisfy this without a copy. */
+typedef struct {
+  const void* const* k; /* HOST array [n_blocks] */
+  const void* const* v;
+  int64_t stride_b, stride_t, stride_p;
+} dfd_kv_taps;
+
+size_t dfd_decoder_workspace_bytes(int B, int T, int D, int n_blocks);
+
+/* mask: uint8 [B,T] (1 = frame present; src/models.py:324). block_out: fp32 [B, n_blocks, D] (x after every
+ * block, the torch.cat of models.py:269). video_feature: fp32 [B, D] = ln_post(block_out[:, -1]) (:340-343). */
+int dfd_decoder_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
+                        const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
+                        float* video_feature, void* workspace, size_t workspace_bytes, void* stream);
+
+/* logits[b,:] = scale * l / (||l||_2 + 1e-10), l = feature[b,:] @ proj[D,O] (models.py:359, 551-553).
+ * scale <= 0 skips the normalisation. */
+int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, int B, int D, int O, float scale,
+                       float* logits, void* stream);
+
+/* One decoder attention call on its own (models.py:136-146 without in/out projections), for unit tests:
+ * qs fp32 [B, H, 128] = per head [smax query(64) | coda query(64)]; mix fp32 [B, H*64]. */
+int dfd_decoder_attention(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
+                          int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
+                          int T, int P, int H, float* mix, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFDCLIP_B200_H_ */
