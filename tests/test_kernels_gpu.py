@@ -113,7 +113,8 @@ def test_patchify(cuda_device, r, patch):
     ref = torch.nn.functional.unfold(x, kernel_size=patch, stride=patch).transpose(1, 2)  # [f, P, 3*p*p] in (c,i,j)
     got = out.view(f, g * g + 1, -1)
     assert got[:, 0].abs().max().item() == 0.0
-    assert got[:, :, k:].abs().max().item() == 0.0
+    if got.shape[-1] > k:
+        assert got[:, :, k:].abs().max().item() == 0.0
     assert torch.equal(got[:, 1:, :k], ref.to(torch.bfloat16))
 
 
