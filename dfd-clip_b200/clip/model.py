@@ -1,0 +1,283 @@
+"""Drop-in for the part of the reference's ``src/clip/model.py`` that DFD-CLIP uses: the CLIP ViT visual tower
+with per-layer q/k/v taps (reference: VisionTransformer src/clip/model.py:254-294, Transformer :229-251,
+ResidualAttentionBlock :202-226, MultiheadAttention :171-199) and ``build_model`` (:453-496).
+
+The modules below only HOLD parameters (same names, shapes and ``state_dict()`` keys as the reference, so the
+decoder initialiser and ``*_weights.pt`` checkpoints work unchanged); the computation is one call into
+libdfdclip_b200.so (``dfd_encoder_forward``): tcgen05 GEMMs, flash-style attention, vectorised LayerNorm.
+There is no PyTorch or CPU fallback: calling ``forward`` without a B200 and the built library raises.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from .. import _native
+
+
+class LayerNorm(nn.LayerNorm):
+    """Parameter holder for a LayerNorm (eps 1e-5); also usable as a module (fp32 math like :157-163)."""
+
+    def forward(self, x):
+        return super().forward(x.float()).to(x.dtype)
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class MultiheadAttention(nn.Module):
+    """Parameter holder: fused in_proj ([3D, D] weight, [3D] bias) and out_proj (reference :171-183)."""
+
+    def __init__(self, embed_dim, n_head):
+        super().__init__()
+        # the reference leaves these uninitialised (torch.empty, :179-180); zeros keep a fresh module finite
+        self.in_proj_weight = nn.Parameter(torch.zeros((3 * embed_dim, embed_dim)))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        self.n_head = n_head
+
+
+class ResidualAttentionBlock(nn.Module):
+    def __init__(self, d_model, n_head, attn_mask=None):
+        super().__init__()
+        self.attn = MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, d_model * 4)),
+            ("gelu", QuickGELU()),
+            ("c_proj", nn.Linear(d_model * 4, d_model)),
+        ]))
+        self.ln_2 = LayerNorm(d_model)
+        self.attn_mask = attn_mask
+
+
+class Transformer(nn.Module):
+    def __init__(self, width, layers, heads, attn_mask=None):
+        super().__init__()
+        self.width = width
+        self.layers = layers
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
+
+
+class VisionTransformer(nn.Module):
+    """CLIP ViT frame encoder. ``forward(x[N,3,R,R], with_out=False, with_q=False)`` returns, like the reference
+    (:276-294, :236-251), one dict per layer with ``k``, ``v`` (and ``q`` / ``out`` on request), each k/v/q a
+    strided ``[N, L, H, 64]`` view of that layer's packed ``[N*L, 3D]`` QKV buffer. Tensors are bf16 (the compute
+    dtype of the B200 path) except ``out`` (fp32 residual stream)."""
+
+    def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.output_dim = output_dim
+        self.width = width
+        self.layers = layers
+        self.heads = heads
+        self.patch_size = patch_size
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads)
+        # present in checkpoints, never applied on this path (reference :273-274 vs :294)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+
+    # ---------------------------------------------------------------------------------------------- native
+    @property
+    def tokens_per_frame(self):
+        return (self.input_resolution // self.patch_size) ** 2 + 1
+
+    def _dims(self):
+        return _native.VitDims(self.input_resolution, self.patch_size, self.width, self.heads, self.layers)
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p in self.parameters())
+
+    def invalidate_packed_weights(self):
+        self._packed = None
+        self._packed_key = None
+
+    def _packed_weights(self):
+        """bf16/fp32 packed copy of the parameters in the library's layout, rebuilt when a parameter changes."""
+        key = self._weights_key()
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        dev = self.conv1.weight.device
+        if dev.type != "cuda":
+            raise _native.NativeError(
+                "dfdclip_b200 VisionTransformer has no CPU path: move the module to a B200 (`.to('cuda')`) first")
+        lib = _native.load_library()
+        dims = self._dims()
+        nbytes = lib.dfd_encoder_packed_bytes(ctypes.byref(dims))
+        if nbytes == 0:
+            raise _native.NativeError("unsupported ViT shape for the B200 path: %s" % _native.load_library()
+                                      .dfd_last_error().decode())
+        params = []  # keep fp32 contiguous views alive until the pack kernels have run
+
+        def f32(t):
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            params.append(t)
+            return t
+
+        blocks = self.transformer.resblocks
+        w = _native.VitWeights()
+        w.conv1_weight = f32(self.conv1.weight).data_ptr()
+        w.class_embedding = f32(self.class_embedding).data_ptr()
+        w.positional_embedding = f32(self.positional_embedding).data_ptr()
+        w.ln_pre_weight = f32(self.ln_pre.weight).data_ptr()
+        w.ln_pre_bias = f32(self.ln_pre.bias).data_ptr()
+        arrays = []
+
+        def per_layer(getter):
+            arr = _native.ptr_array([f32(getter(b)) for b in blocks])
+            arrays.append(arr)
+            return ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+
+        w.ln_1_weight = per_layer(lambda b: b.ln_1.weight)
+        w.ln_1_bias = per_layer(lambda b: b.ln_1.bias)
+        w.in_proj_weight = per_layer(lambda b: b.attn.in_proj_weight)
+        w.in_proj_bias = per_layer(lambda b: b.attn.in_proj_bias)
+        w.out_proj_weight = per_layer(lambda b: b.attn.out_proj.weight)
+        w.out_proj_bias = per_layer(lambda b: b.attn.out_proj.bias)
+        w.ln_2_weight = per_layer(lambda b: b.ln_2.weight)
+        w.ln_2_bias = per_layer(lambda b: b.ln_2.bias)
+        w.c_fc_weight = per_layer(lambda b: b.mlp.c_fc.weight)
+        w.c_fc_bias = per_layer(lambda b: b.mlp.c_fc.bias)
+        w.c_proj_weight = per_layer(lambda b: b.mlp.c_proj.weight)
+        w.c_proj_bias = per_layer(lambda b: b.mlp.c_proj.bias)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.dfd_encoder_pack_weights(_native.ctx(dev), ctypes.byref(dims), ctypes.byref(w),
+                                                       _native.ptr(packed), _native.stream_ptr(dev)))
+            torch.cuda.current_stream(dev).synchronize()  # params/arrays may be temporaries
+        self._packed = packed
+        self._packed_key = key
+        return packed
+
+    def _get_workspace(self, nbytes, dev):
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            self._workspace = None  # release before growing
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._workspace = ws
+        return ws
+
+    def encode(self, x, keep_layers=None, need_out=False, last_qkv_only=None):
+        """Run the encoder on frames x[N,3,R,R] (fp32, cuda). Returns ``(qkv, outs)``: ``qkv[l]`` is the packed
+        bf16 ``[N*L, 3D]`` buffer of layer l for every l in ``keep_layers`` (default: all layers), ``outs[l]`` the
+        fp32 residual stream after layer l when ``need_out``. Layers after the last kept one are not executed, and
+        the last kept layer stops after its QKV projection unless ``need_out`` (dead-work skipping)."""
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
+            raise ValueError("expected frames of shape [N,3,%d,%d], got %s" %
+                             (self.input_resolution, self.input_resolution, tuple(x.shape)))
+        if x.device.type != "cuda":
+            raise _native.NativeError("dfdclip_b200 encoder needs CUDA tensors (no CPU fallback)")
+        lib = _native.load_library()
+        dev = x.device
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        n = x.shape[0]
+        seq, d = self.tokens_per_frame, self.width
+        keep = sorted(set(range(self.layers) if keep_layers is None else keep_layers))
+        if keep and (keep[0] < 0 or keep[-1] >= self.layers):
+            raise IndexError("layer index out of range: %s" % keep)
+        if need_out:
+            run_layers, qkv_only = self.layers, False
+        else:
+            run_layers = (keep[-1] + 1) if keep else 0
+            qkv_only = True if last_qkv_only is None else bool(last_qkv_only)
+        packed = self._packed_weights()
+        dims = self._dims()
+        qkv = {l: torch.empty((n * seq, 3 * d), dtype=torch.bfloat16, device=dev) for l in keep}
+        outs = {l: torch.empty((n, seq, d), dtype=torch.float32, device=dev) for l in range(self.layers)} if need_out else {}
+        if n == 0:
+            return qkv, outs
+        ws_bytes = lib.dfd_encoder_workspace_bytes(ctypes.byref(dims), n)
+        ws = self._get_workspace(ws_bytes, dev)
+        qkv_arr = _native.ptr_array([qkv.get(l) for l in range(self.layers)])
+        out_arr = _native.ptr_array([outs.get(l) for l in range(self.layers)]) if need_out else None
+        with torch.cuda.device(dev):
+            _native.check(lib.dfd_encoder_forward(
+                _native.ctx(dev), ctypes.byref(dims), _native.ptr(packed), _native.ptr(x), n, run_layers,
+                1 if qkv_only else 0, ctypes.cast(qkv_arr, ctypes.POINTER(ctypes.c_void_p)),
+                ctypes.cast(out_arr, ctypes.POINTER(ctypes.c_void_p)) if need_out else None,
+                _native.ptr(ws), ws_bytes, _native.stream_ptr(dev)))
+        return qkv, outs
+
+    def forward(self, x, with_out=False, with_q=False):
+        n = x.shape[0]
+        seq, h = self.tokens_per_frame, self.heads
+        qkv, outs = self.encode(x, keep_layers=None, need_out=with_out, last_qkv_only=False)
+        kvs = []
+        for l in range(self.layers):
+            view = qkv[l].view(n, seq, 3, h, 64)
+            a = dict(k=view[:, :, 1], v=view[:, :, 2])
+            if with_q:
+                a["q"] = view[:, :, 0]
+            if with_out:
+                a["out"] = outs[l]
+            kvs.append(a)
+        return kvs
+
+
+class CLIP(nn.Module):
+    """Holder returned by ``build_model``: only ``.visual`` is implemented (DFD-CLIP takes ``clip.load(..)[0].visual``,
+    src/models.py:440). The text tower / ResNet towers of the reference are out of scope and raise."""
+
+    def __init__(self, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size):
+        super().__init__()
+        if isinstance(vision_layers, (tuple, list)):
+            raise NotImplementedError("ModifiedResNet towers are not part of the DFD-CLIP hot path")
+        vision_heads = vision_width // 64
+        self.visual = VisionTransformer(image_resolution, vision_patch_size, vision_width, vision_layers, vision_heads,
+                                        embed_dim)
+
+    def encode_image(self, image):
+        raise NotImplementedError("CLIP.encode_image (ln_post/proj head) is never used by DFD-CLIP")
+
+    def encode_text(self, text):
+        raise NotImplementedError("the CLIP text tower is out of scope of dfdclip_b200")
+
+    def forward(self, image, text):
+        raise NotImplementedError("CLIP.forward is out of scope of dfdclip_b200")
+
+
+def _fp16_round_(module):
+    """Same rounding ``convert_weights`` applies (reference :429-450): Conv/Linear weights and biases and ``proj``
+    go through fp16; in_proj_* of the custom attention, LayerNorm and embeddings stay fp32."""
+    with torch.no_grad():
+        for m in module.modules():
+            if isinstance(m, (nn.Conv1d, nn.Conv2d, nn.Linear)) and not isinstance(m, nn.LayerNorm):
+                m.weight.copy_(m.weight.half().float())
+                if m.bias is not None:
+                    m.bias.copy_(m.bias.half().float())
+            if isinstance(getattr(m, "proj", None), torch.Tensor):
+                m.proj.copy_(m.proj.half().float())
+
+
+def build_model(state_dict):
+    """Build the (visual-only) CLIP model from a checkpoint state dict, inferring every size from tensor shapes
+    like the reference (:453-496)."""
+    if "visual.proj" not in state_dict:
+        raise NotImplementedError("only ViT CLIP checkpoints are supported (no 'visual.proj' in the state dict)")
+    vision_width = state_dict["visual.conv1.weight"].shape[0]
+    vision_layers = len([k for k in state_dict if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
+    vision_patch_size = state_dict["visual.conv1.weight"].shape[-1]
+    grid_size = round((state_dict["visual.positional_embedding"].shape[0] - 1) ** 0.5)
+    image_resolution = vision_patch_size * grid_size
+    embed_dim = state_dict["visual.proj"].shape[1]
+    model = CLIP(embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size)
+    visual = OrderedDict((k[len("visual."):], v.float()) for k, v in state_dict.items() if k.startswith("visual."))
+    model.visual.load_state_dict(visual)
+    _fp16_round_(model.visual)
+    return model.eval()

@@ -197,8 +197,9 @@ size_t dec_attn_workspace_bytes(int B, int T, int H) {
 int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                       int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B, int T, int P,
                       int H, float* mix, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  DFD_CHECK_ARG(qs && k && v && mask && mix, "decoder_attention: null pointer");
   DFD_CHECK_ARG(B >= 0 && T > 0 && P > 0, "decoder_attention: bad shape B=%d T=%d P=%d", B, T, P);
+  if (B == 0) return 0;
+  DFD_CHECK_ARG(qs && k && v && mask && mix, "decoder_attention: null pointer");
   DFD_CHECK_ARG(H % 4 == 0 && H >= 4 && H <= 16, "decoder_attention: heads=%d unsupported (need 4,8,12,16)", H);
   DFD_CHECK_ARG(stride_p % 8 == 0 && stride_t % 8 == 0 && stride_b % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
@@ -348,9 +349,9 @@ project_logits_kernel(const float* __restrict__ feature, const float* __restrict
 
 int project_logits(const float* feature, const float* proj, int B, int D, int O, float scale, float* logits,
                    cudaStream_t stream) {
-  DFD_CHECK_ARG(feature && proj && logits, "project_logits: null pointer");
   DFD_CHECK_ARG(B >= 0 && D > 0 && O > 0 && O <= 8192, "project_logits: bad shape B=%d D=%d O=%d", B, D, O);
   if (B == 0) return 0;
+  DFD_CHECK_ARG(feature && proj && logits, "project_logits: null pointer");
   project_logits_kernel<<<B, 256, (O + 8) * sizeof(float), stream>>>(feature, proj, D, O, scale, logits);
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
@@ -385,10 +386,10 @@ static DecWs carve_decoder_ws(void* base, int B, int T, int D, int H) {
 int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
                     const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
                     float* video_feature, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  DFD_CHECK_ARG(w && taps && mask && block_out && video_feature, "decoder_forward: null pointer");
   DFD_CHECK_ARG(D == 64 * H, "decoder_forward: width %d != 64 * heads %d", D, H);
   DFD_CHECK_ARG(n_blocks > 0 && B >= 0 && T > 0 && P > 0, "decoder_forward: bad shape");
-  if (B == 0) return 0;
+  if (B == 0) return 0;  // empty batch: nothing to do (buffers of empty tensors are NULL)
+  DFD_CHECK_ARG(w && taps && mask && block_out && video_feature, "decoder_forward: null pointer");
   DecWs ws = carve_decoder_ws(workspace, B, T, D, H);
   if (!workspace || workspace_bytes < ws.total)
     return fail(DFD_ERR_WORKSPACE, "decoder_forward: workspace %zu < %zu bytes", workspace_bytes, ws.total);

@@ -157,8 +157,9 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
                     size_t workspace_bytes, cudaStream_t stream) {
   VitShape s;
   DFD_TRY(vit_shape(dims, &s));
-  DFD_CHECK_ARG(packed && frames, "encoder_forward: null pointer");
   DFD_CHECK_ARG(n_frames >= 0, "encoder_forward: negative frame count");
+  if (n_frames == 0) return 0;
+  DFD_CHECK_ARG(packed && frames, "encoder_forward: null pointer");
   DFD_CHECK_ARG(num_run_layers >= 0 && num_run_layers <= s.layers, "encoder_forward: num_run_layers=%d out of range",
                 num_run_layers);
   if (n_frames == 0) return 0;

@@ -1,0 +1,347 @@
+"""Drop-in for the encoder/head interface of the reference's ``src/models.py``: ``Detector`` (:394-780) and
+``Decoder`` (:272-361) with the same constructor, methods, attributes and ``state_dict()`` key schema
+(SURVEY App. B.3), computing on the B200 through libdfdclip_b200.so.
+
+Supported configuration = the reference's defaults (``Detector.get_default_config`` :406-431): CLIP foundation,
+stride or index taps, ``op_mode.temporal_position`` on or off, no adapter, empty ``train_mode``. Every other knob
+raises ``NotImplementedError`` instead of silently diverging. There is no CPU / PyTorch fallback for the encoder
+or the decoder attention.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import _native, clip
+from .config import CN
+
+_UNSUPPORTED_OP_MODES = ("attn_mode", "global_prediction", "aug_query", "ema_frame")
+
+
+def auc_roc(weight=None, label_smoothing=0.0, *args, **kargs):
+    """Per-sample cross entropy on the normalised logits (reference :34-45)."""
+
+    def driver(logits, y, _weight=weight, _label_smoothing=label_smoothing):
+        if _weight:
+            _weight = torch.tensor(_weight, device=logits.device)
+        return torch.nn.functional.cross_entropy(logits, y, weight=_weight, label_smoothing=_label_smoothing,
+                                                 reduction="none")
+
+    return driver
+
+
+_LOSSES = {"auc_roc": auc_roc}
+
+
+def disable_gradients(module: nn.Module):
+    for params in module.parameters():
+        params.requires_grad = False
+    return module
+
+
+class LayerNorm(nn.LayerNorm):
+    def forward(self, x):
+        return super().forward(x.float()).to(x.dtype)
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class MultiheadAttention(nn.Module):
+    """Parameter holder of the decoder attention: ``in_proj`` D -> 2D (per head [smax query | coda query],
+    reference :129-137) and ``out_proj``. K and V are the encoder taps, never projected."""
+
+    def __init__(self, config, num_frames, embed_dim, n_head):
+        super().__init__()
+        self.num_frames = num_frames
+        self.n_act = 2
+        self.in_proj = nn.Linear(embed_dim, self.n_act * embed_dim)
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        self.embed_dim = embed_dim
+        self.n_head = n_head
+
+
+class ResidualAttentionBlock(nn.Module):
+    def __init__(self, d_model, n_head, config, num_frames, block_index, layer_indices, reference_layers):
+        super().__init__()
+        self.attn = MultiheadAttention(config, num_frames, d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, d_model * 4)),
+            ("gelu", QuickGELU()),
+            ("dropout", nn.Dropout(config.dropout)),
+            ("c_proj", nn.Linear(d_model * 4, d_model)),
+        ]))
+        self.ln_2 = LayerNorm(d_model)
+        self._apply_reference(config, block_index, layer_indices, reference_layers)
+
+    def _apply_reference(self, config, block_index, layer_indices, reference_layers):
+        """Initialise ln_1 / ln_2 / mlp from the tapped CLIP layer (reference :178-229)."""
+        current = layer_indices[block_index]
+        self.ln_1.load_state_dict(reference_layers[current].ln_1.state_dict())
+        self.ln_2.load_state_dict(reference_layers[current].ln_2.state_dict())
+        mlp_layer = current
+        if "concat_ref" in config and config.concat_ref and block_index < len(layer_indices) - 1:
+            mlp_layer = layer_indices[block_index + 1] - 1
+        src = reference_layers[mlp_layer].mlp.state_dict()
+        self.mlp.load_state_dict(src)
+
+
+class Transformer(nn.Module):
+    def __init__(self, width, heads, config, num_frames, layer_indices, reference_layers):
+        super().__init__()
+        self.width = width
+        self.resblocks = nn.Sequential(*[
+            ResidualAttentionBlock(width, heads, config, num_frames, i, layer_indices, reference_layers)
+            for i in range(len(layer_indices))
+        ])
+
+
+class Decoder(nn.Module):
+    """Temporal decoder: a learnable CLS query cross-attends (softmax + CoDA) to the tapped K/V of all T*P patch
+    tokens of a clip, block by block, then ``ln_post`` and the task projection(s) (reference :272-361)."""
+
+    def __init__(self, detector, config, num_frames):
+        super().__init__()
+        width = detector.encoder.width
+        heads = detector.encoder.heads
+        self.width, self.heads, self.num_frames = width, heads, num_frames
+        self.op_mode = config.op_mode
+        for key in _UNSUPPORTED_OP_MODES:
+            if key in config.op_mode and config.op_mode[key]:
+                raise NotImplementedError("op_mode.%s is not implemented by the B200 path" % key)
+        if config.dropout:
+            raise NotImplementedError("dropout > 0 is not implemented by the B200 path")
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        if "temporal_position" in config.op_mode and config.op_mode.temporal_position:
+            self.positional_embedding = nn.Parameter(scale * torch.randn(num_frames, 1, heads, width // heads))
+        else:
+            self.positional_embedding = None
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, heads, config, num_frames, layer_indices=detector.layer_indices,
+                                       reference_layers=detector.encoder.transformer.resblocks)
+        self.ln_post = LayerNorm(width)
+        self.task_projections = []
+        for i, output_dim in enumerate(config.out_dim):
+            name = f"proj{i}x{output_dim}"
+            setattr(self, name, nn.Parameter(scale * torch.randn(width, output_dim)))
+            self.task_projections.append([getattr(self, name)])
+        self._wcache = None
+        self._workspace = None
+
+    # ------------------------------------------------------------------------------------------ native
+    def _native_weights(self):
+        """``dfd_decoder_weights`` struct of fp32 device pointers (parameters are used in place, not copied)."""
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), str(p.device), p.dtype) for p in params)
+        if self._wcache is not None and self._wcache[0] == key:
+            return self._wcache[1]
+        for p in params:
+            if p.device.type != "cuda" or p.dtype != torch.float32 or not p.is_contiguous():
+                raise _native.NativeError("decoder parameters must be contiguous fp32 CUDA tensors "
+                                          "(dfdclip_b200 has no CPU path; call .to('cuda') / .float())")
+        blocks = self.transformer.resblocks
+        w = _native.DecoderWeights()
+        keep = []
+
+        def arr(getter):
+            a = _native.ptr_array([getter(b) for b in blocks])
+            keep.append(a)
+            return ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p))
+
+        w.class_embedding = self.class_embedding.data_ptr()
+        w.positional_embedding = None if self.positional_embedding is None else self.positional_embedding.data_ptr()
+        w.ln_pre_weight, w.ln_pre_bias = self.ln_pre.weight.data_ptr(), self.ln_pre.bias.data_ptr()
+        w.ln_post_weight, w.ln_post_bias = self.ln_post.weight.data_ptr(), self.ln_post.bias.data_ptr()
+        w.ln_1_weight, w.ln_1_bias = arr(lambda b: b.ln_1.weight), arr(lambda b: b.ln_1.bias)
+        w.in_proj_weight, w.in_proj_bias = arr(lambda b: b.attn.in_proj.weight), arr(lambda b: b.attn.in_proj.bias)
+        w.out_proj_weight, w.out_proj_bias = arr(lambda b: b.attn.out_proj.weight), arr(lambda b: b.attn.out_proj.bias)
+        w.ln_2_weight, w.ln_2_bias = arr(lambda b: b.ln_2.weight), arr(lambda b: b.ln_2.bias)
+        w.c_fc_weight, w.c_fc_bias = arr(lambda b: b.mlp.c_fc.weight), arr(lambda b: b.mlp.c_fc.bias)
+        w.c_proj_weight, w.c_proj_bias = arr(lambda b: b.mlp.c_proj.weight), arr(lambda b: b.mlp.c_proj.bias)
+        self._wcache = (key, w, keep)
+        return w
+
+    def forward(self, kvs, m):
+        """kvs: list (one per tapped layer) of ``{k, v: [B, T, P, H, 64]}``; m: bool [B, T].
+        Returns ``(task_logits, video_feature)`` like the reference (:323-361); logits are NOT yet normalised."""
+        return self.run(kvs, m, logit_scale=0.0)
+
+    def run(self, kvs, m, logit_scale=0.0):
+        """``forward`` with the logit normalisation of ``Detector.predict`` (:551-553) fused into the projection
+        kernel when ``logit_scale`` > 0."""
+        if len(kvs) != len(self.transformer.resblocks):
+            raise ValueError("expected %d tapped layers, got %d" % (len(self.transformer.resblocks), len(kvs)))
+        k0 = kvs[0]["k"]
+        if k0.dim() != 5 or k0.shape[3] != self.heads or k0.shape[4] != 64:
+            raise ValueError("expected K/V of shape [B,T,P,%d,64], got %s" % (self.heads, tuple(k0.shape)))
+        b, t, p = k0.shape[:3]
+        if self.positional_embedding is not None and t != self.positional_embedding.shape[0]:
+            raise ValueError("clip has %d frames but the decoder was built for %d" %
+                             (t, self.positional_embedding.shape[0]))
+        dev = k0.device
+        if dev.type != "cuda":
+            raise _native.NativeError("dfdclip_b200 decoder needs CUDA tensors (no CPU fallback)")
+        strides = None
+        ks, vs, keep = [], [], []
+        for kv in kvs:
+            pair = []
+            for name in ("k", "v"):
+                ten = kv[name].detach()
+                ok = (ten.dtype == torch.bfloat16 and ten.shape == k0.shape and ten.stride(4) == 1 and ten.stride(3) == 64
+                      and all(s % 8 == 0 for s in ten.stride()[:3]) and ten.data_ptr() % 16 == 0
+                      and (strides is None or ten.stride()[:3] == strides))
+                if not ok:
+                    ten = ten.to(torch.bfloat16).contiguous()
+                    if strides is not None and ten.stride()[:3] != strides:
+                        raise ValueError("all tapped K/V tensors must share one layout")
+                if strides is None:
+                    strides = ten.stride()[:3]
+                keep.append(ten)
+                pair.append(ten)
+            ks.append(pair[0])
+            vs.append(pair[1])
+        lib = _native.load_library()
+        nb, d = len(kvs), self.width
+        w = self._native_weights()
+        karr, varr = _native.ptr_array(ks), _native.ptr_array(vs)
+        taps = _native.KvTaps(ctypes.cast(karr, ctypes.POINTER(ctypes.c_void_p)),
+                              ctypes.cast(varr, ctypes.POINTER(ctypes.c_void_p)), strides[0], strides[1], strides[2])
+        mask = m.to(device=dev, dtype=torch.uint8).contiguous()
+        if mask.shape != (b, t):
+            raise ValueError("mask shape %s does not match clips [%d, %d]" % (tuple(mask.shape), b, t))
+        block_out = torch.empty((b, nb, d), dtype=torch.float32, device=dev)
+        video_feature = torch.empty((b, d), dtype=torch.float32, device=dev)
+        ws_bytes = lib.dfd_decoder_workspace_bytes(b, t, d, nb)
+        if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
+            self._workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.dfd_decoder_forward(
+                _native.ctx(dev), d, self.heads, nb, ctypes.byref(w), ctypes.byref(taps), _native.ptr(mask), b, t, p,
+                _native.ptr(block_out), _native.ptr(video_feature), _native.ptr(self._workspace), ws_bytes,
+                _native.stream_ptr(dev)))
+            task_logits = [_native.project_logits(video_feature, mats[-1].detach(), scale=logit_scale)
+                           for mats in self.task_projections]
+        self.last_block_outputs = block_out
+        return task_logits, video_feature
+
+
+class Detector(nn.Module):
+    """Deepfake video detector: frozen CLIP ViT frame encoder -> per-layer K/V taps -> temporal decoder
+    (reference :394-780). Same constructor and methods as the reference class."""
+
+    @staticmethod
+    def get_default_config():
+        C = CN(new_allowed=True)
+        C.name = "Detector"
+        C.foundation = "clip"
+        C.architecture = "ViT-B/16"
+        C.decode_mode = "stride"
+        C.decode_stride = 2
+        C.decode_indices = []
+        C.out_dim = []
+        C.losses = []
+        C.concat_ref = 0
+        C.adapter = CN(new_allowed=True)
+        C.adapter.type = "none"
+        C.train_mode = CN(new_allowed=True)
+        C.op_mode = CN(new_allowed=True)
+        C.op_mode.temporal_position = 1
+        C.dropout = 0.0
+        C.weight_decay = 0.01
+        C.optimizer = "sgd"
+        return C
+
+    def __init__(self, config, num_frames, accelerator=None):
+        super().__init__()
+        assert config.decode_mode in ["stride", "index"]
+        self.config = config
+        if config.foundation != "clip":
+            raise NotImplementedError("foundation=%r: only the CLIP backbone is implemented on the B200 path" %
+                                      (config.foundation,))
+        if config.adapter.type != "none":
+            raise NotImplementedError("adapter.type=%r is not implemented by the B200 path" % (config.adapter.type,))
+        if len(config.train_mode) > 0:
+            raise NotImplementedError("train_mode %s is not implemented by the B200 path" % (list(config.train_mode),))
+        if accelerator is not None and hasattr(accelerator, "main_process_first"):
+            with accelerator.main_process_first():
+                self.encoder = disable_gradients(clip.load(config.architecture, device="cpu")[0].visual.float())
+        else:
+            self.encoder = disable_gradients(clip.load(config.architecture, device="cpu")[0].visual.float())
+        self.decode_mode = config.decode_mode
+        self.out_dim = config.out_dim
+        self.weight_decay = config.weight_decay
+        self.optimizer = config.optimizer
+        self.train_mode = config.train_mode
+        self.op_mode = config.op_mode
+        self.losses = []
+        for loss in config.losses:
+            if isinstance(loss, str):
+                name, kwargs = loss, {}
+            else:
+                name, kwargs = loss.name, (dict(loss.args) if "args" in loss else {})
+            if name not in _LOSSES:
+                raise NotImplementedError("loss %r is not implemented by the B200 path" % (name,))
+            self.losses.append(_LOSSES[name](**kwargs))
+        if self.decode_mode == "stride":
+            self.layer_indices = list(range(0, len(self.encoder.transformer.resblocks), config.decode_stride))
+        else:
+            self.layer_indices = list(config.decode_indices)
+        self.decoder = Decoder(self, config, num_frames)
+        self.adapter = None
+        self.transform = self._transform(self.encoder.input_resolution)
+
+    # --------------------------------------------------------------------------------------------- predict
+    def predict(self, x, m, with_video_features=False, with_adapt_features=False, train=False):
+        """x fp32 [B,T,3,R,R] (normalised frames), m bool [B,T] -> ``(task_logits, features)`` with
+        ``task_logits[i] = 5 * l / (||l||_2 + 1e-10)`` (reference :498-566)."""
+        if with_adapt_features:
+            raise Exception("cannot return adaptive features without an adapter")
+        b, t = x.shape[:2]
+        seq, h = self.encoder.tokens_per_frame, self.encoder.heads
+        with torch.no_grad():
+            qkv, _ = self.encoder.encode(x.flatten(0, 1), keep_layers=self.layer_indices)
+            kvs = []
+            for layer in self.layer_indices:
+                view = qkv[layer].view(b, t, seq, 3, h, 64)
+                # discard the CLS token, restore the temporal dimension (:505-507)
+                kvs.append(dict(k=view[:, :, 1:, 1], v=view[:, :, 1:, 2]))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()) and train:
+            raise NotImplementedError("the decoder backward (training step) is not implemented yet on the B200 path")
+        task_logits, video_features = self.decoder.run(kvs, m, logit_scale=5.0)
+        features = {}
+        if with_video_features:
+            features["video"] = video_features
+        return task_logits, features
+
+    def forward(self, x, y, m, comp=None, speed=None, train=False, single_task=None, *args, **kargs):
+        """Eval: ``(task_losses, task_logits)``; train adds ``other_losses`` (reference :568-596, 738)."""
+        task_logits, features = self.predict(x, m, with_video_features=True, train=train)
+        task_losses = [
+            loss_fn(logits, labels) if single_task is None or i == single_task else 0
+            for i, loss_fn, logits, labels in zip(range(len(self.losses)), self.losses, task_logits, y)
+        ]
+        if not train:
+            return task_losses, task_logits
+        return task_losses, task_logits, {}
+
+    def configure_optimizers(self, lr):
+        params = [i for i in self.parameters() if i.requires_grad]
+        if self.optimizer == "sgd":
+            return torch.optim.SGD(params=params, lr=lr, weight_decay=self.weight_decay, momentum=0.95)
+        elif self.optimizer == "adamw":
+            return torch.optim.AdamW(params=params, lr=lr, weight_decay=self.weight_decay)
+
+    def _transform(self, n_px):
+        """CPU-side frame preprocessing of the data loader (reference :756-768); not on the hot path."""
+        import torchvision.transforms as T
+        return T.Compose([
+            T.Resize(n_px, interpolation=T.InterpolationMode.BICUBIC),
+            T.CenterCrop(n_px),
+            T.ConvertImageDtype(torch.float32),
+            T.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)),
+        ])

@@ -1,0 +1,163 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (``/root/reference``) in this container.
+
+ORACLE / test infrastructure. The reference is pure Python and cannot travel to the GPU box, so its outputs on
+seeded synthetic inputs are committed as small fixtures, together with this script (``python oracle/gen_golden.py``).
+
+How the reference is run without modification:
+  * ``yacs`` and ``ftfy`` are not installed: tiny stand-ins are injected into ``sys.modules`` (a dict-with-attributes
+    ``CfgNode``; ``ftfy.fix_text`` = identity — the tokenizer is imported by ``src/clip`` but never used);
+  * ``Detector.__init__`` calls ``clip.load(config.architecture)``: a TorchScript archive of a parameter-holder
+    module whose ``state_dict()`` has CLIP's keys is written to a temp dir, so the reference's own loader and
+    ``build_model`` (fp16 rounding included) build the encoder;
+  * the full ``Detector`` state dict from ``dfdclip_b200.synthetic`` is then loaded with the reference's strict
+    ``load_state_dict`` — the route ``inference.py:99`` takes with ``*_weights.pt``.
+"""
+import contextlib
+import os
+import sys
+import tempfile
+import types
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = os.environ.get("DFD_REFERENCE", "/root/reference")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from dfdclip_b200 import synthetic  # noqa: E402  (weights/clips factory shared with tests and bench)
+
+# name -> (arch, T, B, full K/V stored?)
+CASES = {
+    "tiny": ("tiny-256x4", 4, 3, True),
+    "small": ("small-512x6", 3, 2, False),
+    "vitb16": ("ViT-B/16", 8, 2, False),
+    "vitl14": ("ViT-L/14", 4, 1, False),
+}
+N_SAMPLES = 4096
+
+
+def install_stubs():
+    class CfgNode(dict):
+        def __init__(self, init_dict=None, key_list=None, new_allowed=False):
+            super().__init__(init_dict or {})
+
+        def __getattr__(self, name):
+            try:
+                return self[name]
+            except KeyError:
+                raise AttributeError(name)
+
+        def __setattr__(self, name, value):
+            self[name] = value
+
+    yacs = types.ModuleType("yacs")
+    yacs_config = types.ModuleType("yacs.config")
+    yacs_config.CfgNode = CfgNode
+    yacs.config = yacs_config
+    sys.modules.setdefault("yacs", yacs)
+    sys.modules.setdefault("yacs.config", yacs_config)
+    ftfy = types.ModuleType("ftfy")
+    ftfy.fix_text = lambda text: text
+    sys.modules.setdefault("ftfy", ftfy)
+
+
+class FakeAccelerator:
+    device = torch.device("cpu")
+
+    @contextlib.contextmanager
+    def main_process_first(self):
+        yield
+
+
+def write_jit_holder(state_dict, path):
+    """TorchScript archive of empty modules carrying `state_dict` as buffers under the same dotted names."""
+    root = torch.nn.Module()
+    for key, tensor in state_dict.items():
+        mod = root
+        parts = key.split(".")
+        for part in parts[:-1]:
+            if not hasattr(mod, part):
+                mod.add_module(part, torch.nn.Module())
+            mod = getattr(mod, part)
+        mod.register_buffer(parts[-1], tensor.clone())
+    torch.jit.script(root).save(path)
+
+
+def sample_indices(numel, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, numel, (min(N_SAMPLES, numel),), generator=g)
+
+
+def run_case(name, arch, num_frames, batch, full):
+    from src.models import Detector  # the reference's own class
+
+    dims = synthetic.vit_dims(arch)
+    tmp = tempfile.mkdtemp(prefix="dfd_golden_")
+    ckpt = os.path.join(tmp, "clip_%s.pt" % name)
+    write_jit_holder(synthetic.clip_checkpoint_state_dict(arch, seed=0), ckpt)
+
+    cfg = Detector.get_default_config()
+    cfg.architecture = ckpt
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    torch.manual_seed(1)
+    det = Detector(cfg, num_frames, FakeAccelerator())
+    os.remove(ckpt)
+
+    sd = synthetic.detector_state_dict(arch, num_frames, out_dims=(2,), taps=det.layer_indices, seed=0)
+    # the encoder built by the reference's clip.load/build_model must equal the synthetic fp32 values exactly
+    # (they are fp16-representable where build_model rounds)
+    for k, v in det.encoder.state_dict().items():
+        assert torch.equal(v, sd["encoder." + k]), "encoder weight mismatch after the reference loader: " + k
+    missing = det.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    det.eval()
+
+    x, m = synthetic.make_clips(batch, num_frames, dims["image_size"], seed=7)
+    labels = torch.arange(batch) % 2
+    with torch.no_grad():
+        taps = det.encoder(x.flatten(0, 1), with_out=True, with_q=True)
+        logits, feats = det.predict(x, m, with_video_features=True)
+        losses, logits2 = det(x, [labels], m, single_task=0)
+    assert torch.equal(logits[0], logits2[0])
+
+    out = {
+        "arch": np.array(arch), "num_frames": np.array(num_frames), "batch": np.array(batch),
+        "layer_indices": np.array(det.layer_indices), "mask": m.numpy(), "labels": labels.numpy(),
+        "logits": logits[0].numpy(), "video_feature": feats["video"].numpy(), "losses": losses[0].numpy(),
+        "pred_labels": logits[0].argmax(-1).numpy(),
+    }
+    for i, a in enumerate(taps):
+        for key in ("q", "k", "v", "out"):
+            t = a[key].contiguous().float()
+            out["norm_%s_%d" % (key, i)] = np.array(t.norm().item(), dtype=np.float64)
+            if full:
+                out["%s_%d" % (key, i)] = t.numpy()
+            else:
+                idx = sample_indices(t.numel(), seed=1000 * i + {"q": 0, "k": 1, "v": 2, "out": 3}[key])
+                out["idx_%s_%d" % (key, i)] = idx.numpy()
+                out["val_%s_%d" % (key, i)] = t.flatten()[idx].numpy()
+    path = os.path.join(GOLDEN_DIR, "reference_%s.npz" % name)
+    np.savez_compressed(path, **out)
+    print("%-8s %-12s logits=%s labels=%s -> %s (%.1f KiB)" % (
+        name, arch, np.round(out["logits"], 4).tolist(), out["pred_labels"].tolist(), os.path.relpath(path, ROOT),
+        os.path.getsize(path) / 1024))
+
+
+def main(argv):
+    warnings.filterwarnings("ignore")
+    install_stubs()
+    sys.path.insert(0, REFERENCE)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    for name, (arch, t, b, full) in CASES.items():
+        if len(argv) > 1 and name not in argv[1:]:
+            continue
+        run_case(name, arch, t, b, full)
+
+
+if __name__ == "__main__":
+    main(sys.argv)

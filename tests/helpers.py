@@ -1,0 +1,57 @@
+"""Shared test helpers: golden-vector loading, the oracle import, and north_star tolerances."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# BASELINE.json north_star tolerances for the bf16 CUDA path against the reference's fp32 path
+TOL_FEATURE_COSINE = 0.999   # per-layer features (K/V taps)
+TOL_LOGIT_ABS = 2e-2         # clip logits, absolute
+
+
+def load_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dfd_oracle
+    return dfd_oracle
+
+
+def load_golden(name):
+    data = np.load(os.path.join(GOLDEN_DIR, "reference_%s.npz" % name))
+    out = {k: data[k] for k in data.files}
+    out["arch"] = str(out["arch"])
+    out["num_frames"] = int(out["num_frames"])
+    out["batch"] = int(out["batch"])
+    out["layer_indices"] = [int(i) for i in out["layer_indices"]]
+    return out
+
+
+def golden_inputs(g):
+    """The exact (state_dict, clips, mask) the golden generator fed the reference."""
+    from dfdclip_b200 import synthetic
+    dims = synthetic.vit_dims(g["arch"])
+    sd = synthetic.detector_state_dict(g["arch"], g["num_frames"], out_dims=(2,), taps=g["layer_indices"], seed=0)
+    x, m = synthetic.make_clips(g["batch"], g["num_frames"], dims["image_size"], seed=7)
+    assert np.array_equal(m.numpy(), g["mask"])
+    return sd, x, m
+
+
+def golden_tensor(g, key, layer, like):
+    """Golden values for tap `key` of `layer`: (reference values, matching values taken from `like`)."""
+    like = like.contiguous().float().cpu()
+    full = "%s_%d" % (key, layer)
+    if full in g:
+        return torch.from_numpy(g[full]), like
+    idx = torch.from_numpy(g["idx_%s_%d" % (key, layer)])
+    return torch.from_numpy(g["val_%s_%d" % (key, layer)]), like.flatten()[idx]
+
+
+def cosine(a, b):
+    a, b = a.flatten().double(), b.flatten().double()
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()

@@ -1,0 +1,73 @@
+"""CPU tests (-m "not gpu"): pin the oracle restatement (oracle/dfd_oracle.py) to golden vectors produced by the
+UNMODIFIED reference (oracle/gen_golden.py, run in the build container where /root/reference exists)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import cosine, golden_inputs, golden_tensor, load_golden, load_oracle
+
+CASES = ["tiny", "small", "vitb16", "vitl14"]
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return load_oracle()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_golden(oracle, case):
+    g = load_golden(case)
+    sd, x, m = golden_inputs(g)
+    with torch.no_grad():
+        enc = oracle.encoder_forward(sd, x.flatten(0, 1), with_out=True, with_q=True)
+        logits, feat = oracle.detector_predict(sd, x, m, g["layer_indices"], (2,))
+    # per-layer q/k/v/out of every encoder layer: fp32 restatement of the same torch ops -> ~1e-5
+    for layer, a in enumerate(enc):
+        for key in ("q", "k", "v", "out"):
+            ref, got = golden_tensor(g, key, layer, a[key])
+            scale = ref.abs().max().item()
+            assert (got - ref).abs().max().item() <= 2e-4 * max(scale, 1.0), (case, layer, key)
+            assert abs(a[key].float().norm().item() / float(g["norm_%s_%d" % (key, layer)]) - 1) < 1e-5
+    assert np.abs(logits[0].numpy() - g["logits"]).max() < 1e-4
+    assert np.abs(feat.numpy() - g["video_feature"]).max() < 2e-4
+    assert np.array_equal(logits[0].argmax(-1).numpy(), g["pred_labels"])
+    losses = oracle.detector_eval_losses(logits, [torch.from_numpy(g["labels"])])
+    assert np.abs(losses[0].numpy() - g["losses"]).max() < 1e-4
+
+
+def test_logits_have_norm_five(oracle):
+    g = load_golden("tiny")
+    assert np.allclose(np.linalg.norm(g["logits"], axis=-1), 5.0, atol=1e-4)
+
+
+def test_masked_frames_do_not_matter(oracle):
+    """Frames masked out by m must not influence the clip logits (src/models.py:104, 124)."""
+    g = load_golden("tiny")
+    sd, x, m = golden_inputs(g)
+    assert not m.all()
+    x2 = x.clone()
+    x2[~m] = torch.randn_like(x2[~m]) * 10
+    with torch.no_grad():
+        a, _ = oracle.detector_predict(sd, x, m, g["layer_indices"], (2,))
+        b, _ = oracle.detector_predict(sd, x2, m, g["layer_indices"], (2,))
+    assert torch.allclose(a[0], b[0], atol=1e-5)
+
+
+def test_all_masked_clip_is_nan(oracle):
+    """An all-masked clip gives NaN in the reference (softmax over all -inf, SURVEY 8c caveat 4)."""
+    qs = torch.randn(1, 1, 4, 128)
+    k = torch.randn(1, 6, 4, 64)
+    out = oracle.decoder_attention(qs, k, k, torch.zeros(1, 6, dtype=torch.bool))
+    assert torch.isnan(out).all()
+
+
+def test_video_scores_mean_of_probs(oracle):
+    logits = torch.tensor([[5.0, 0.0], [0.0, 5.0], [3.0, 4.0]])
+    s = oracle.video_scores(logits, [2, 1])
+    assert torch.allclose(s[0], logits[:2].softmax(-1).mean(0))
+    assert torch.allclose(s[1], logits[2].softmax(-1))
+
+
+def test_cosine_helper():
+    a = torch.randn(100)
+    assert abs(cosine(a, a) - 1) < 1e-12

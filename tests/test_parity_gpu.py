@@ -1,0 +1,165 @@
+"""GPU parity tests proper: the drop-in Detector / VisionTransformer / Decoder (CUDA path through the C ABI)
+against (1) golden vectors of the unmodified reference and (2) the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's north_star: per-layer features cosine >= 0.999, clip logits within 2e-2 absolute,
+identical predicted labels (the CUDA path computes the encoder in bf16 with fp32 accumulation, the reference fp32).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (TOL_FEATURE_COSINE, TOL_LOGIT_ABS, cosine, golden_inputs, golden_tensor, load_golden,
+                     load_oracle)
+
+pytestmark = pytest.mark.gpu
+
+
+def build_detector(arch, num_frames, layer_indices, device, sd=None, decode_indices=None):
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.models import Detector
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:" + arch
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    if decode_indices is not None:
+        cfg.decode_mode = "index"
+        cfg.decode_indices = list(decode_indices)
+    det = Detector(cfg, num_frames, None)
+    if sd is None:
+        sd = synthetic.detector_state_dict(arch, num_frames, out_dims=(2,), taps=det.layer_indices, seed=0)
+    det.load_state_dict(sd, strict=True)
+    assert det.layer_indices == list(layer_indices)
+    return det.to(device).eval(), sd
+
+
+@pytest.mark.parametrize("case", ["tiny", "small", "vitb16", "vitl14"])
+def test_detector_predict_matches_reference_golden(cuda_device, case):
+    g = load_golden(case)
+    sd, x, m = golden_inputs(g)
+    det, _ = build_detector(g["arch"], g["num_frames"], g["layer_indices"], cuda_device, sd)
+    logits, feats = det.predict(x.to(cuda_device), m.to(cuda_device), with_video_features=True)
+    torch.cuda.synchronize()
+    got = logits[0].cpu().numpy()
+    assert got.shape == g["logits"].shape
+    err = np.abs(got - g["logits"]).max()
+    assert err <= TOL_LOGIT_ABS, f"{case}: max |dlogit| {err:.4f}"
+    assert np.array_equal(got.argmax(-1), g["pred_labels"])
+    assert np.allclose(np.linalg.norm(got, axis=-1), 5.0, atol=1e-3)
+    assert cosine(feats["video"].cpu(), torch.from_numpy(g["video_feature"])) >= TOL_FEATURE_COSINE
+    # eval forward: per-sample cross entropy on the normalised logits (src/models.py:590-596)
+    labels = torch.from_numpy(g["labels"]).to(cuda_device)
+    losses, logits2 = det(x.to(cuda_device), [labels], m.to(cuda_device), single_task=0)
+    assert np.abs(losses[0].cpu().numpy() - g["losses"]).max() <= 2 * TOL_LOGIT_ABS
+    assert torch.equal(logits2[0], logits[0])
+
+
+@pytest.mark.parametrize("case", ["tiny", "small", "vitb16", "vitl14"])
+def test_encoder_taps_match_reference_golden(cuda_device, case):
+    """VisionTransformer.forward(x, with_out=True, with_q=True): every layer's q/k/v/out (model.py:236-251)."""
+    g = load_golden(case)
+    sd, x, m = golden_inputs(g)
+    det, _ = build_detector(g["arch"], g["num_frames"], g["layer_indices"], cuda_device, sd)
+    kvs = det.encoder(x.flatten(0, 1).to(cuda_device), with_out=True, with_q=True)
+    torch.cuda.synchronize()
+    n = x.shape[0] * x.shape[1]
+    assert len(kvs) == det.encoder.layers
+    for layer, a in enumerate(kvs):
+        assert tuple(a["k"].shape) == (n, det.encoder.tokens_per_frame, det.encoder.heads, 64)
+        for key in ("q", "k", "v", "out"):
+            ref, got = golden_tensor(g, key, layer, a[key])
+            c = cosine(got, ref)
+            assert c >= TOL_FEATURE_COSINE, f"{case} layer {layer} {key}: cosine {c:.5f}"
+            rel = ((got - ref).norm() / ref.norm()).item()
+            assert rel < 3e-2, f"{case} layer {layer} {key}: rel err {rel:.4f}"
+
+
+def test_predict_against_oracle_with_masks_and_index_taps(cuda_device):
+    """Same seeded inputs through the CPU oracle and the CUDA path; taps chosen by index (decode_mode='index')."""
+    from dfdclip_b200 import synthetic
+    oracle = load_oracle()
+    arch, t, b = "small-512x6", 5, 7
+    taps = [1, 2, 5]
+    det, sd = build_detector(arch, t, taps, cuda_device, decode_indices=taps)
+    x, m = synthetic.make_clips(b, t, synthetic.vit_dims(arch)["image_size"], seed=11)
+    m[2, 1:] = False  # a clip with a single valid frame
+    with torch.no_grad():
+        ref_logits, ref_feat, ref_taps = oracle.detector_predict(sd, x, m, taps, (2,), return_taps=True)
+    logits, feats = det.predict(x.to(cuda_device), m.to(cuda_device), with_video_features=True)
+    torch.cuda.synchronize()
+    assert (logits[0].cpu() - ref_logits[0]).abs().max().item() <= TOL_LOGIT_ABS
+    assert torch.equal(logits[0].cpu().argmax(-1), ref_logits[0].argmax(-1))
+    assert cosine(feats["video"].cpu(), ref_feat) >= TOL_FEATURE_COSINE
+    # per-layer tapped features
+    qkv, _ = det.encoder.encode(x.flatten(0, 1).to(cuda_device), keep_layers=taps)
+    seq, h = det.encoder.tokens_per_frame, det.encoder.heads
+    for i, layer in enumerate(taps):
+        view = qkv[layer].view(b, t, seq, 3, h, 64)
+        for j, key in ((1, "k"), (2, "v")):
+            c = cosine(view[:, :, 1:, j].float().cpu(), ref_taps[i][key])
+            assert c >= TOL_FEATURE_COSINE, (layer, key, c)
+
+
+def test_masked_frames_do_not_matter_cuda(cuda_device):
+    from dfdclip_b200 import synthetic
+    arch, t, b = "tiny-256x4", 4, 4
+    det, _ = build_detector(arch, t, [0, 2], cuda_device)
+    x, m = synthetic.make_clips(b, t, 32, seed=3)
+    assert not m.all()
+    x2 = x.clone()
+    x2[~m] = 100.0
+    a, _ = det.predict(x.to(cuda_device), m.to(cuda_device))
+    c, _ = det.predict(x2.to(cuda_device), m.to(cuda_device))
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], c[0])
+
+
+def test_batch_independence_and_determinism(cuda_device):
+    """Clips are independent units: a clip's logits do not depend on its batch mates; reruns are bit-identical."""
+    from dfdclip_b200 import synthetic
+    arch, t, b = "tiny-256x4", 4, 6
+    det, _ = build_detector(arch, t, [0, 2], cuda_device)
+    x, m = synthetic.make_clips(b, t, 32, seed=5)
+    x, m = x.to(cuda_device), m.to(cuda_device)
+    full, _ = det.predict(x, m)
+    again, _ = det.predict(x, m)
+    part, _ = det.predict(x[2:5], m[2:5])
+    torch.cuda.synchronize()
+    assert torch.equal(full[0], again[0])
+    assert torch.equal(full[0][2:5], part[0])
+
+
+def test_empty_batch(cuda_device):
+    det, _ = build_detector("tiny-256x4", 4, [0, 2], cuda_device)
+    x = torch.zeros(0, 4, 3, 32, 32, device=cuda_device)
+    m = torch.zeros(0, 4, dtype=torch.bool, device=cuda_device)
+    logits, _ = det.predict(x, m)
+    assert tuple(logits[0].shape) == (0, 2)
+
+
+def test_unsupported_configs_raise(cuda_device):
+    from dfdclip_b200.models import Detector
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:tiny-256x4"
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    cfg.op_mode.global_prediction = 1
+    with pytest.raises(NotImplementedError):
+        Detector(cfg, 4, None)
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:tiny-256x4"
+    cfg.adapter.type = "normal"
+    with pytest.raises(NotImplementedError):
+        Detector(cfg, 4, None)
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA tensors, never fall back to PyTorch/CPU."""
+    import dfdclip_b200._native as nat
+    det_cfg = None
+    from dfdclip_b200.models import Detector
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:tiny-256x4"
+    cfg.out_dim = [2]
+    det = Detector(cfg, 4, None).eval()
+    with pytest.raises(nat.NativeError):
+        det.predict(torch.zeros(1, 4, 3, 32, 32), torch.ones(1, 4, dtype=torch.bool))
