@@ -22,6 +22,7 @@ EXPORTS = (
     "dfd_gemm_bf16", "dfd_layernorm", "dfd_patchify", "dfd_mha_fwd",
     "dfd_encoder_packed_bytes", "dfd_encoder_workspace_bytes", "dfd_encoder_pack_weights", "dfd_encoder_forward",
     "dfd_decoder_workspace_bytes", "dfd_decoder_forward", "dfd_project_logits", "dfd_decoder_attention",
+    "dfd_timing_enable", "dfd_timing_read", "dfd_timing_num_tags", "dfd_timing_tag_name",
 )
 
 
@@ -101,6 +102,10 @@ def load_library():
         lib.dfd_decoder_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                               c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                               c_size_t, c_void_p]
+        lib.dfd_timing_enable.argtypes = [c_void_p, c_int]
+        lib.dfd_timing_read.argtypes = [c_void_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_int)]
+        lib.dfd_timing_tag_name.argtypes = [c_int]
+        lib.dfd_timing_tag_name.restype = ctypes.c_char_p
         for name in EXPORTS:
             fn = getattr(lib, name)
             if fn.restype is c_int and name not in ("dfd_version",):
@@ -132,6 +137,21 @@ def ctx(device):
         with _lib_lock:
             _ctxs[index] = handle
     return handle
+
+
+def timing_enable(device, on=True):
+    """Bracket every kernel of the encoder/decoder calls with CUDA events (see dfd_timing_* in the header)."""
+    check(load_library().dfd_timing_enable(ctx(device), 1 if on else 0))
+
+
+def timing_read(device):
+    """{kernel tag: (total_ms, launches)} accumulated since the last read; synchronises on the events."""
+    lib = load_library()
+    n = lib.dfd_timing_num_tags()
+    ms = (c_float * n)()
+    cnt = (c_int * n)()
+    check(lib.dfd_timing_read(ctx(device), n, ms, cnt))
+    return {lib.dfd_timing_tag_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
 
 
 def stream_ptr(device=None):

@@ -76,8 +76,60 @@ int dfd_ctx_create(int device, dfd_ctx** out) {
 
 int dfd_ctx_destroy(dfd_ctx* ctx) {
   dfd::clear_error();
+  if (ctx) {
+    for (auto& s : ctx->slots) {
+      cudaEventDestroy(s.start);
+      cudaEventDestroy(s.stop);
+    }
+  }
   delete ctx;
   return 0;
+}
+
+int dfd_timing_enable(dfd_ctx* ctx, int on) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_timing_enable: ctx is NULL");
+  if (on && ctx->slots.empty()) {
+    ctx->slots.resize(8192);
+    for (auto& s : ctx->slots) {
+      DFD_CUDA_OK(cudaEventCreate(&s.start));
+      DFD_CUDA_OK(cudaEventCreate(&s.stop));
+    }
+  }
+  ctx->slots_used = 0;
+  ctx->timing = on != 0;
+  return 0;
+}
+
+int dfd_timing_read(dfd_ctx* ctx, int max_tags, float* total_ms, int* counts) {
+  dfd::clear_error();
+  if (!ctx || !total_ms || !counts) return dfd::fail(DFD_ERR_INVALID, "dfd_timing_read: null pointer");
+  const int n = max_tags < DFD_TAG_COUNT ? max_tags : DFD_TAG_COUNT;
+  for (int i = 0; i < n; ++i) {
+    total_ms[i] = 0.f;
+    counts[i] = 0;
+  }
+  for (size_t i = 0; i < ctx->slots_used; ++i) {
+    const auto& s = ctx->slots[i];
+    DFD_CUDA_OK(cudaEventSynchronize(s.stop));
+    float ms = 0.f;
+    DFD_CUDA_OK(cudaEventElapsedTime(&ms, s.start, s.stop));
+    if (s.tag < n) {
+      total_ms[s.tag] += ms;
+      counts[s.tag] += 1;
+    }
+  }
+  ctx->slots_used = 0;
+  return DFD_OK;
+}
+
+int dfd_timing_num_tags(void) { return DFD_TAG_COUNT; }
+
+const char* dfd_timing_tag_name(int tag) {
+  static const char* names[DFD_TAG_COUNT] = {"patchify",  "gemm_patch_embed", "layernorm",  "gemm_qkv",
+                                             "mha",       "gemm_out_proj",    "gemm_c_fc",  "gemm_c_proj",
+                                             "dec_attn",  "dec_linear",       "dec_other"};
+  return (tag >= 0 && tag < DFD_TAG_COUNT) ? names[tag] : "?";
 }
 
 }  // extern "C"

@@ -394,6 +394,11 @@ int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_de
   if (!workspace || workspace_bytes < ws.total)
     return fail(DFD_ERR_WORKSPACE, "decoder_forward: workspace %zu < %zu bytes", workspace_bytes, ws.total);
   const int nthr = 256, nblk = (B * D + nthr - 1) / nthr;
+#define DFD_TIMED(tag, call)          \
+  do {                                \
+    ScopedTimer _t(ctx, tag, stream); \
+    DFD_TRY(call);                    \
+  } while (0)
 
   // x = ln_pre(class_embedding) repeated for every clip (models.py:336-337; dropout p = 0)
   DFD_TRY(layernorm(w->class_embedding, w->ln_pre_weight, w->ln_pre_bias, nullptr, 0, nullptr, ws.y, 1, D, stream));
@@ -402,16 +407,23 @@ int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_de
 
   for (int i = 0; i < n_blocks; ++i) {
     // x = x + out_proj(attn(in_proj(ln_1(x)), K_i, V_i, m))        (models.py:173-174, 136-146)
-    DFD_TRY(layernorm(ws.x, w->ln_1_weight[i], w->ln_1_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
-    DFD_TRY(linear_f32(ws.y, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, ws.qs, B, 2 * D, D, false, stream));
-    DFD_TRY(decoder_attention(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
-                              w->positional_embedding, mask, B, T, P, H, ws.mix, ws.part,
-                              dec_attn_workspace_bytes(B, T, H), stream));
-    DFD_TRY(linear_f32(ws.mix, w->out_proj_weight[i], w->out_proj_bias[i], ws.x, ws.x, B, D, D, false, stream));
+    DFD_TIMED(DFD_TAG_DEC_OTHER,
+              layernorm(ws.x, w->ln_1_weight[i], w->ln_1_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
+    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ws.y, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, ws.qs, B, 2 * D,
+                                             D, false, stream));
+    DFD_TIMED(DFD_TAG_DEC_ATTN,
+              decoder_attention(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
+                                w->positional_embedding, mask, B, T, P, H, ws.mix, ws.part,
+                                dec_attn_workspace_bytes(B, T, H), stream));
+    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ws.mix, w->out_proj_weight[i], w->out_proj_bias[i], ws.x, ws.x, B, D, D,
+                                             false, stream));
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                     (models.py:175)
-    DFD_TRY(layernorm(ws.x, w->ln_2_weight[i], w->ln_2_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
-    DFD_TRY(linear_f32(ws.y, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, ws.hid, B, 4 * D, D, true, stream));
-    DFD_TRY(linear_f32(ws.hid, w->c_proj_weight[i], w->c_proj_bias[i], ws.x, ws.x, B, D, 4 * D, false, stream));
+    DFD_TIMED(DFD_TAG_DEC_OTHER,
+              layernorm(ws.x, w->ln_2_weight[i], w->ln_2_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
+    DFD_TIMED(DFD_TAG_DEC_LINEAR,
+              linear_f32(ws.y, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, ws.hid, B, 4 * D, D, true, stream));
+    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ws.hid, w->c_proj_weight[i], w->c_proj_bias[i], ws.x, ws.x, B, D, 4 * D,
+                                             false, stream));
     scatter_block_out_kernel<<<nblk, nthr, 0, stream>>>(ws.x, block_out, B, D, i, n_blocks);
     DFD_CUDA_OK(cudaGetLastError());
   }

@@ -181,27 +181,37 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
   auto f32p = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
 
   // stem: conv1 as a GEMM over the patch matrix (cls rows are zero rows), then cls/pos add fused into ln_pre
-  DFD_TRY(patchify(frames, patches, n_frames, s.R, s.p, s.Kp, stream));
-  DFD_TRY(gemm_bf16(ctx, patches, s.Kp, pk + pl.conv_w, s.Kp, nullptr, x, D, M, D, s.Kp, DFD_EPI_STORE_F32, stream));
-  DFD_TRY(layernorm(x, f32p(pl.ln_pre_w), f32p(pl.ln_pre_b), f32p(pl.posc), s.L, nullptr, x, M, D, stream));
+#define DFD_TIMED(tag, call)              \
+  do {                                    \
+    ScopedTimer _t(ctx, tag, stream);     \
+    DFD_TRY(call);                        \
+  } while (0)
+  DFD_TIMED(DFD_TAG_PATCHIFY, patchify(frames, patches, n_frames, s.R, s.p, s.Kp, stream));
+  DFD_TIMED(DFD_TAG_GEMM_PATCH,
+            gemm_bf16(ctx, patches, s.Kp, pk + pl.conv_w, s.Kp, nullptr, x, D, M, D, s.Kp, DFD_EPI_STORE_F32, stream));
+  DFD_TIMED(DFD_TAG_LAYERNORM,
+            layernorm(x, f32p(pl.ln_pre_w), f32p(pl.ln_pre_b), f32p(pl.posc), s.L, nullptr, x, M, D, stream));
 
   for (int l = 0; l < num_run_layers; ++l) {
     const size_t lb = pl.layer0 + pl.layer_stride * l;
     void* qkv = (qkv_out && qkv_out[l]) ? qkv_out[l] : static_cast<void*>(ws + wl.qkv);
     // a = attn(ln_1(x))
-    DFD_TRY(layernorm(x, f32p(lb + pl.ln1_w), f32p(lb + pl.ln1_b), nullptr, 0, u, nullptr, M, D, stream));
-    DFD_TRY(gemm_bf16(ctx, u, D, pk + lb + pl.w_in, D, f32p(lb + pl.b_in), qkv, 3 * D, M, 3 * D, D, DFD_EPI_STORE_BF16,
-                      stream));
+    DFD_TIMED(DFD_TAG_LAYERNORM,
+              layernorm(x, f32p(lb + pl.ln1_w), f32p(lb + pl.ln1_b), nullptr, 0, u, nullptr, M, D, stream));
+    DFD_TIMED(DFD_TAG_GEMM_QKV, gemm_bf16(ctx, u, D, pk + lb + pl.w_in, D, f32p(lb + pl.b_in), qkv, 3 * D, M, 3 * D, D,
+                                          DFD_EPI_STORE_BF16, stream));
     if (l == num_run_layers - 1 && last_qkv_only) break;
-    DFD_TRY(mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
+    DFD_TIMED(DFD_TAG_MHA, mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
     // x = x + out_proj(mix)
-    DFD_TRY(gemm_bf16(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D, DFD_EPI_ADD_F32, stream));
+    DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
+                                          DFD_EPI_ADD_F32, stream));
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))
-    DFD_TRY(layernorm(x, f32p(lb + pl.ln2_w), f32p(lb + pl.ln2_b), nullptr, 0, u, nullptr, M, D, stream));
-    DFD_TRY(gemm_bf16(ctx, u, D, pk + lb + pl.w_fc, D, f32p(lb + pl.b_fc), hid, 4 * D, M, 4 * D, D,
-                      DFD_EPI_STORE_BF16_QGELU, stream));
-    DFD_TRY(gemm_bf16(ctx, hid, 4 * D, pk + lb + pl.w_proj, 4 * D, f32p(lb + pl.b_proj), x, D, M, D, 4 * D,
-                      DFD_EPI_ADD_F32, stream));
+    DFD_TIMED(DFD_TAG_LAYERNORM,
+              layernorm(x, f32p(lb + pl.ln2_w), f32p(lb + pl.ln2_b), nullptr, 0, u, nullptr, M, D, stream));
+    DFD_TIMED(DFD_TAG_GEMM_FC, gemm_bf16(ctx, u, D, pk + lb + pl.w_fc, D, f32p(lb + pl.b_fc), hid, 4 * D, M, 4 * D, D,
+                                         DFD_EPI_STORE_BF16_QGELU, stream));
+    DFD_TIMED(DFD_TAG_GEMM_PROJ, gemm_bf16(ctx, hid, 4 * D, pk + lb + pl.w_proj, 4 * D, f32p(lb + pl.b_proj), x, D, M,
+                                           D, 4 * D, DFD_EPI_ADD_F32, stream));
     if (x_out && x_out[l])
       DFD_CUDA_OK(cudaMemcpyAsync(x_out[l], x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
   }

@@ -11,11 +11,38 @@
 
 #include "../../include/dfdclip_b200.h"
 
+#include <vector>
+
+// Optional per-kernel timing (dfd_timing_*): CUDA event pairs recorded on the launching stream around each
+// kernel of the hot path, accumulated per tag. Off by default.
+enum {
+  DFD_TAG_PATCHIFY = 0,
+  DFD_TAG_GEMM_PATCH,
+  DFD_TAG_LAYERNORM,
+  DFD_TAG_GEMM_QKV,
+  DFD_TAG_MHA,
+  DFD_TAG_GEMM_OUT,
+  DFD_TAG_GEMM_FC,
+  DFD_TAG_GEMM_PROJ,
+  DFD_TAG_DEC_ATTN,
+  DFD_TAG_DEC_LINEAR,
+  DFD_TAG_DEC_OTHER,
+  DFD_TAG_COUNT
+};
+
+struct dfd_timing_slot {
+  int tag;
+  cudaEvent_t start, stop;
+};
+
 struct dfd_ctx {
   int device;
   int num_sms;
   int smem_optin;
   void* encode_tiled;  // PFN_cuTensorMapEncodeTiled
+  mutable bool timing = false;
+  mutable std::vector<dfd_timing_slot> slots;
+  mutable size_t slots_used = 0;
 };
 
 namespace dfd {
@@ -47,5 +74,22 @@ void clear_error();
 // 128-byte swizzle (box_cols * elem_bytes must be 128).
 int make_tmap_2d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
                  uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+
+// RAII event pair around one kernel launch (no-op unless timing is enabled on the context).
+struct ScopedTimer {
+  const dfd_ctx* ctx;
+  cudaStream_t stream;
+  dfd_timing_slot* slot = nullptr;
+  ScopedTimer(const dfd_ctx* c, int tag, cudaStream_t s) : ctx(c), stream(s) {
+    if (c && c->timing && c->slots_used < c->slots.size()) {
+      slot = &c->slots[c->slots_used++];
+      slot->tag = tag;
+      cudaEventRecord(slot->start, stream);
+    }
+  }
+  ~ScopedTimer() {
+    if (slot) cudaEventRecord(slot->stop, stream);
+  }
+};
 
 }  // namespace dfd

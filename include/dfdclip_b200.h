@@ -50,6 +50,14 @@ const char* dfd_last_error(void);
 int dfd_ctx_create(int device, dfd_ctx** out);
 int dfd_ctx_destroy(dfd_ctx* ctx);
 
+/* Optional per-kernel timing for bench.py's roofline: when enabled, every kernel launch of the encoder/decoder
+ * calls is bracketed by a CUDA event pair on the launching stream. dfd_timing_read synchronises on those events,
+ * returns per-tag total milliseconds and launch counts (arrays of dfd_timing_num_tags() entries) and clears them. */
+int dfd_timing_enable(dfd_ctx* ctx, int on);
+int dfd_timing_read(dfd_ctx* ctx, int max_tags, float* total_ms, int* counts);
+int dfd_timing_num_tags(void);
+const char* dfd_timing_tag_name(int tag);
+
 /* ------------------------------------------------------------------------------------------------------
  * Unit kernels (exported so each can be parity-tested on its own).
  * ---------------------------------------------------------------------------------------------------- */

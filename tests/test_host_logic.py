@@ -1,0 +1,253 @@
+"""CPU tests (-m "not gpu") of the host side: C-ABI library exports, the drop-in loader / Detector interface
+(construction, state_dict schema, error behaviour), the video-level scoring driver incl. a world_size-2 gloo run."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from helpers import ROOT, load_oracle
+
+
+# ------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    import dfdclip_b200._native as nat
+    header = open(os.path.join(ROOT, "include", "dfdclip_b200.h")).read()
+    declared = set(re.findall(r"\b(dfd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dfd_ctx"}
+    assert declared, "no declarations parsed"
+    lib = nat.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libdfdclip_b200.so does not export " + name
+    assert declared == set(nat.EXPORTS), (declared ^ set(nat.EXPORTS))
+    assert lib.dfd_version() == 1
+
+
+def test_native_refuses_without_gpu():
+    import dfdclip_b200._native as nat
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(nat.NativeError):
+        nat.ctx("cuda:0")
+
+
+def test_workspace_size_queries_do_not_need_a_gpu():
+    import ctypes
+    import dfdclip_b200._native as nat
+    lib = nat.load_library()
+    dims = nat.VitDims(224, 16, 768, 12, 12)
+    packed = lib.dfd_encoder_packed_bytes(ctypes.byref(dims))
+    # 12 layers x 12*D*D bf16 + conv + fp32 vectors: ~171 MB
+    assert 170e6 < packed < 175e6
+    ws = lib.dfd_encoder_workspace_bytes(ctypes.byref(dims), 512)
+    assert ws >= 512 * 197 * 768 * (4 + 2 + 2 + 8 + 6)
+    bad = nat.VitDims(224, 16, 700, 12, 12)
+    assert lib.dfd_encoder_packed_bytes(ctypes.byref(bad)) == 0
+    assert lib.dfd_decoder_workspace_bytes(64, 8, 768, 6) > 0
+
+
+# ------------------------------------------------------------------------------- loader / Detector surface
+def _detector(arch="tiny-256x4", frames=4, **over):
+    from dfdclip_b200.models import Detector
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:" + arch
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    for k, v in over.items():
+        cfg[k] = v
+    return Detector(cfg, frames, None), cfg
+
+
+def test_state_dict_schema_matches_reference_vitb16():
+    """231 fp32 tensors for ViT-B/16 with 6 decoder blocks; names as in the reference."""
+    from dfdclip_b200 import synthetic
+    sd = synthetic.detector_state_dict("ViT-B/16", 8)
+    assert len(sd) == 231
+    assert sd["encoder.transformer.resblocks.11.attn.in_proj_weight"].shape == (2304, 768)
+    assert sd["decoder.transformer.resblocks.5.attn.in_proj.weight"].shape == (1536, 768)
+    assert sd["decoder.positional_embedding"].shape == (8, 1, 12, 64)
+    assert sd["decoder.proj0x2"].shape == (768, 2)
+    assert all(v.dtype == torch.float32 for v in sd.values())
+
+
+def test_detector_surface_and_state_dict_roundtrip():
+    from dfdclip_b200 import synthetic
+    det, cfg = _detector()
+    assert det.layer_indices == [0, 2]
+    assert det.out_dim == [2]
+    assert det.encoder.input_resolution == 32 and det.encoder.patch_size == 16
+    assert det.encoder.width == 256 and det.encoder.heads == 4 and det.encoder.layers == 4
+    assert not any(p.requires_grad for p in det.encoder.parameters())
+    assert all(p.requires_grad for p in det.decoder.parameters())
+    sd = synthetic.detector_state_dict("tiny-256x4", 4)
+    assert set(det.state_dict().keys()) == set(sd.keys())
+    det.load_state_dict(sd, strict=True)
+    for k, v in det.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    opt = det.configure_optimizers(0.1)
+    assert isinstance(opt, torch.optim.SGD)
+    n_trainable = sum(p.numel() for g in opt.param_groups for p in g["params"])
+    assert n_trainable == sum(p.numel() for p in det.decoder.parameters())
+    assert callable(det.transform)
+
+
+def test_decoder_initialised_from_tapped_clip_layers():
+    """Decoder block i copies ln_1 / ln_2 / mlp of encoder layer layer_indices[i] (src/models.py:178-229)."""
+    det, _ = _detector()
+    for i, layer in enumerate(det.layer_indices):
+        enc, dec = det.encoder.transformer.resblocks[layer], det.decoder.transformer.resblocks[i]
+        assert torch.equal(enc.ln_1.weight, dec.ln_1.weight)
+        assert torch.equal(enc.mlp.c_fc.weight, dec.mlp.c_fc.weight)
+        assert torch.equal(enc.mlp.c_proj.bias, dec.mlp.c_proj.bias)
+
+
+def test_index_decode_mode_and_unsupported_knobs():
+    det, _ = _detector(decode_mode="index", decode_indices=[1, 3])
+    assert det.layer_indices == [1, 3]
+    from dfdclip_b200.models import Detector
+    for mutate in (lambda c: c.op_mode.__setitem__("attn_mode", "frame"),
+                   lambda c: c.op_mode.__setitem__("aug_query", 1),
+                   lambda c: c.adapter.__setitem__("type", "normal"),
+                   lambda c: c.__setitem__("foundation", "dinov2"),
+                   lambda c: c.__setitem__("dropout", 0.1),
+                   lambda c: c.train_mode.__setitem__("temporal", "ranking")):
+        cfg = Detector.get_default_config()
+        cfg.architecture = "synthetic:tiny-256x4"
+        cfg.out_dim = [2]
+        mutate(cfg)
+        with pytest.raises(NotImplementedError):
+            Detector(cfg, 4, None)
+
+
+def test_clip_load_from_checkpoint_files(tmp_path):
+    """clip.load accepts a plain torch.save(state_dict) file and a TorchScript holder archive (clip.py:121-139);
+    build_model applies the reference's fp16 rounding to conv/linear/proj only (model.py:429-450)."""
+    from dfdclip_b200 import clip, synthetic
+    sd = synthetic.clip_checkpoint_state_dict("tiny-256x4", seed=3)
+    noisy = {k: v.clone() for k, v in sd.items()}
+    noisy["visual.conv1.weight"] += 1e-5  # not fp16 representable any more
+    noisy["visual.transformer.resblocks.0.attn.in_proj_weight"] += 1e-5
+    path = str(tmp_path / "ckpt.pt")
+    torch.save(noisy, path)
+    model, preprocess = clip.load(path, device="cpu")
+    v = model.visual
+    assert torch.equal(v.conv1.weight, noisy["visual.conv1.weight"].half().float())
+    key = "visual.transformer.resblocks.0.attn.in_proj_weight"
+    assert torch.equal(v.transformer.resblocks[0].attn.in_proj_weight, noisy[key])  # NOT rounded
+    assert torch.equal(v.class_embedding, sd["visual.class_embedding"])
+    assert callable(preprocess)
+    # TorchScript holder route
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gen_golden
+    jit_path = str(tmp_path / "ckpt_jit.pt")
+    gen_golden.write_jit_holder(sd, jit_path)
+    model2, _ = clip.load(jit_path, device="cpu")
+    assert torch.equal(model2.visual.proj, sd["visual.proj"])
+    with pytest.raises(RuntimeError):
+        clip.load("no-such-model")
+    assert "ViT-B/16" in clip.available_models()
+
+
+def test_predict_without_cuda_raises_not_falls_back():
+    import dfdclip_b200._native as nat
+    det, _ = _detector()
+    with pytest.raises(nat.NativeError):
+        det.predict(torch.zeros(1, 4, 3, 32, 32), torch.ones(1, 4, dtype=torch.bool))
+    with pytest.raises(nat.NativeError):
+        det.encoder(torch.zeros(2, 3, 32, 32))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dfd-clip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "dfd_oracle" not in text and "import oracle" not in text, f
+
+
+# --------------------------------------------------------------------------------- video-level scoring driver
+def test_shard_videos_balanced_and_complete():
+    from dfdclip_b200.inference import shard_videos
+    rng = np.random.default_rng(3)
+    counts = rng.integers(8, 33, size=560).tolist()  # config C3: 560 videos, 8..32 clips each
+    for world in (1, 2, 4, 8):
+        shards = shard_videos(counts, world)
+        assert sorted(i for s in shards for i in s) == list(range(560))
+        loads = [sum(counts[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= 32
+    assert shard_videos([], 4) == [[], [], [], []]
+
+
+def test_video_mean_probs_matches_oracle():
+    from dfdclip_b200.inference import video_mean_probs
+    oracle = load_oracle()
+    g = torch.Generator().manual_seed(0)
+    counts = [3, 1, 7, 2]
+    logits = torch.randn(sum(counts), 2, generator=g) * 3
+    assert torch.allclose(video_mean_probs(logits, counts), oracle.video_scores(logits, counts), atol=1e-6)
+
+
+def _fake_predict(x, m):
+    # deterministic stand-in for Detector.predict on CPU: logits from masked frame means
+    w = m.float().unsqueeze(-1)
+    feat = (x.flatten(2).mean(-1, keepdim=True) * w).sum(1) / w.sum(1).clamp_min(1)
+    return torch.cat([feat, -feat], dim=-1) * 5
+
+
+def _make_videos(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    counts = torch.randint(0, 6, (n,), generator=g).tolist()
+    counts[0] = 0  # an empty video (skipped by the reference, inference.py:109-111)
+    videos = [torch.randn(c, 3, 3, 4, 4, generator=g) for c in counts]
+    masks = [torch.ones(c, 3, dtype=torch.bool) for c in counts]
+    return videos, masks, counts
+
+
+def test_score_videos_single_process():
+    from dfdclip_b200.inference import score_videos
+    videos, masks, counts = _make_videos(9)
+    out = score_videos(_fake_predict, videos, masks, chunk_clips=2)
+    assert out.shape == (9, 2)
+    for i, c in enumerate(counts):
+        if c == 0:
+            assert torch.isnan(out[i]).all()
+        else:
+            ref = _fake_predict(videos[i], masks[i]).softmax(-1).mean(0)
+            assert torch.allclose(out[i], ref, atol=1e-6)
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from dfdclip_b200.inference import score_videos
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        videos, masks, _ = _make_videos(11, seed=5)
+        out = score_videos(_fake_predict, videos, masks, chunk_clips=2)
+        ret[rank] = out.numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_score_videos_two_ranks_gloo_matches_single_process():
+    from dfdclip_b200.inference import score_videos
+    videos, masks, _ = _make_videos(11, seed=5)
+    single = score_videos(_fake_predict, videos, masks, chunk_clips=2).numpy()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as manager:
+        ret = manager.dict()
+        port = 29500 + (os.getpid() % 2000)
+        procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=240)
+            assert p.exitcode == 0
+        for r in range(2):
+            assert np.array_equal(ret[r], single, equal_nan=True)  # bit-identical on every rank
