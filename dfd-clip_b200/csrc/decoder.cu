@@ -18,7 +18,6 @@ int layernorm(const float* x, const float* gamma, const float* beta, const float
               float* out_f32, int64_t rows, int D, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------ decoder attention (partial)
-constexpr int DEC_WARPS = 8;
 constexpr int DEC_REC = 130;  // per (clip, frame, head): m, l, acc0[64], acc1[64]
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
@@ -38,16 +37,21 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
   return r;
 }
 
-// NCH = H/4: 16-byte chunks of one K (or V) row handled by each lane; lane l, slot j covers head 4j + l/8,
-// channels (l%8)*8 .. +8.
-template <int NCH>
-__global__ void __launch_bounds__(DEC_WARPS * 32, 1)
+// One CTA per (clip, frame). Warp w handles head group hg = w % (H/4) (4 heads: lane l covers head 4*hg + l/8,
+// channels (l%8)*8 .. +8, i.e. one 16-byte piece of the K row and one of the V row per key) and every KS-th key
+// starting at ks = w / (H/4). A warp-wide load therefore reads 512 contiguous bytes of the token's K (or V) row.
+// Keys are processed UNROLL at a time so that 2*UNROLL independent 16-byte loads per lane are in flight.
+constexpr int DEC_UNROLL = 3;
+
+template <int H>
+__global__ void __launch_bounds__(384, 2)
 dec_attn_partial_kernel(const float* __restrict__ qs, const __nv_bfloat16* __restrict__ kbase,
                         const __nv_bfloat16* __restrict__ vbase, int64_t stride_b, int64_t stride_t, int64_t stride_p,
                         const float* __restrict__ pos_emb, const uint8_t* __restrict__ mask, int T, int P,
                         float* __restrict__ part) {
-  constexpr int H = NCH * 4;
-  extern __shared__ float dsm[];  // [DEC_WARPS][H][DEC_REC]
+  constexpr int HG = H / 4;                      // head groups
+  constexpr int KS = (H == 4) ? 8 : (H == 8 ? 4 : (H == 12 ? 4 : 3));  // key subsets; warps = HG * KS
+  extern __shared__ float dsm[];                 // [KS][H][DEC_REC]
   const int b = blockIdx.x / T, t = blockIdx.x % T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* out = part + (static_cast<int64_t>(blockIdx.x) * H) * DEC_REC;
@@ -57,112 +61,102 @@ dec_attn_partial_kernel(const float* __restrict__ qs, const __nv_bfloat16* __res
     for (int i = threadIdx.x; i < H * DEC_REC; i += blockDim.x) out[i] = (i % DEC_REC == 0) ? -INFINITY : 0.f;
     return;
   }
+  const int hg = warp % HG, ks = warp / HG;
+  const int head = hg * 4 + (lane >> 3), d0 = (lane & 7) * 8;
 
-  float q0[NCH][8], q1[NCH][8], pe[NCH][8], acc0[NCH][8], acc1[NCH][8], m[NCH], l[NCH];
-#pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const int head = j * 4 + (lane >> 3), d0 = (lane & 7) * 8;
+  float q0[8], q1[8], pe[8], acc0[8], acc1[8];
+  {
     const float* qh = qs + (static_cast<int64_t>(b) * H + head) * 128;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      q0[j][e] = qh[d0 + e];
-      q1[j][e] = qh[64 + d0 + e];
-      pe[j][e] = pos_emb ? pos_emb[(static_cast<int64_t>(t) * H + head) * 64 + d0 + e] : 0.f;
-      acc0[j][e] = 0.f;
-      acc1[j][e] = 0.f;
+      q0[e] = qh[d0 + e];
+      q1[e] = qh[64 + d0 + e];
+      pe[e] = pos_emb ? pos_emb[(static_cast<int64_t>(t) * H + head) * 64 + d0 + e] : 0.f;
+      acc0[e] = 0.f;
+      acc1[e] = 0.f;
     }
-    m[j] = -INFINITY;
-    l[j] = 0.f;
   }
+  float m = -INFINITY, l = 0.f;
+  const int64_t off = b * stride_b + t * stride_t + hg * 256 + lane * 8;
+  const __nv_bfloat16* kf = kbase + off;
+  const __nv_bfloat16* vf = vbase + off;
 
-  const __nv_bfloat16* kf = kbase + b * stride_b + t * stride_t + lane * 8;
-  const __nv_bfloat16* vf = vbase + b * stride_b + t * stride_t + lane * 8;
-
-  constexpr int KB = 2;  // keys in flight per warp iteration
-  for (int p0 = warp * KB; p0 < P; p0 += DEC_WARPS * KB) {
-    uint4 kraw[KB][NCH], vraw[KB][NCH];
+  for (int p0 = ks; p0 < P; p0 += KS * DEC_UNROLL) {
+    uint4 kraw[DEC_UNROLL], vraw[DEC_UNROLL];
 #pragma unroll
-    for (int u = 0; u < KB; ++u) {
-      const int p = min(p0 + u, P - 1);
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        kraw[u][j] = ldg_stream16(kf + p * stride_p + j * 256);
-        vraw[u][j] = ldg_stream16(vf + p * stride_p + j * 256);
-      }
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const int p = min(p0 + u * KS, P - 1);
+      kraw[u] = ldg_stream16(kf + p * stride_p);
+      vraw[u] = ldg_stream16(vf + p * stride_p);
     }
 #pragma unroll
-    for (int u = 0; u < KB; ++u) {
-      if (p0 + u < P) {
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      if (p0 + u * KS < P) {
+        float kk[8], vv[8];
+        bf16x8_to_float(kraw[u], kk);
+        bf16x8_to_float(vraw[u], vv);
+        float d0s = 0.f, d1s = 0.f, l1s = 0.f;
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          float kk[8], vv[8];
-          bf16x8_to_float(kraw[u][j], kk);
-          bf16x8_to_float(vraw[u][j], vv);
-          float d0 = 0.f, d1 = 0.f, l1 = 0.f;
+        for (int e = 0; e < 8; ++e) {
+          const float kt = kk[e] + pe[e];
+          d0s = fmaf(q0[e], kt, d0s);
+          d1s = fmaf(q1[e], kt, d1s);
+          l1s += fabsf(q1[e] - kt);
+          vv[e] += pe[e];
+        }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float kt = kk[e] + pe[j][e];
-            d0 = fmaf(q0[j][e], kt, d0);
-            d1 = fmaf(q1[j][e], kt, d1);
-            l1 += fabsf(q1[j][e] - kt);
-            vv[e] += pe[j][e];
-          }
+        for (int o = 1; o < 8; o <<= 1) {
+          d0s += __shfl_xor_sync(0xffffffffu, d0s, o);
+          d1s += __shfl_xor_sync(0xffffffffu, d1s, o);
+          l1s += __shfl_xor_sync(0xffffffffu, l1s, o);
+        }
+        const float s0 = d0s * 0.125f;
+        const float mn = fmaxf(m, s0);
+        const float resc = __expf(m - mn);  // first key: exp(-inf) = 0
+        const float pr = __expf(s0 - mn);
+        m = mn;
+        l = l * resc + pr;
+        // tanh(x) = 1 - 2/(1+exp(2x));  2*sigmoid(-y) = 2/(1+exp(y))
+        const float th = 1.f - 2.f / (1.f + __expf(0.25f * d1s));
+        const float a1 = th * (2.f / (1.f + __expf(0.125f * l1s)));
 #pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-            l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-          }
-          const float s0 = d0 * 0.125f;
-          const float mn = fmaxf(m[j], s0);
-          const float resc = __expf(m[j] - mn);  // first key: exp(-inf) = 0
-          const float pr = __expf(s0 - mn);
-          m[j] = mn;
-          l[j] = l[j] * resc + pr;
-          // tanh(x) = 1 - 2/(1+exp(2x));  2*sigmoid(-y) = 2/(1+exp(y))
-          const float th = 1.f - 2.f / (1.f + __expf(0.25f * d1));
-          const float a1 = th * (2.f / (1.f + __expf(0.125f * l1)));
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            acc0[j][e] = fmaf(acc0[j][e], resc, pr * vv[e]);
-            acc1[j][e] = fmaf(a1, vv[e], acc1[j][e]);
-          }
+        for (int e = 0; e < 8; ++e) {
+          acc0[e] = fmaf(acc0[e], resc, pr * vv[e]);
+          acc1[e] = fmaf(a1, vv[e], acc1[e]);
         }
       }
     }
   }
 
-  // ---- combine the 8 warps of this CTA
-#pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const int head = j * 4 + (lane >> 3), d0 = (lane & 7) * 8;
-    float* rec = dsm + (static_cast<int64_t>(warp) * H + head) * DEC_REC;
+  // ---- combine the KS key subsets of this CTA
+  {
+    float* rec = dsm + (static_cast<int64_t>(ks) * H + head) * DEC_REC;
     if ((lane & 7) == 0) {
-      rec[0] = m[j];
-      rec[1] = l[j];
+      rec[0] = m;
+      rec[1] = l;
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      rec[2 + d0 + e] = acc0[j][e];
-      rec[66 + d0 + e] = acc1[j][e];
+      rec[2 + d0 + e] = acc0[e];
+      rec[66 + d0 + e] = acc1[e];
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < H * 64; i += blockDim.x) {
-    const int head = i >> 6, d = i & 63;
+    const int hh = i >> 6, d = i & 63;
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) M = fmaxf(M, dsm[(w * H + head) * DEC_REC]);
+    for (int w = 0; w < KS; ++w) M = fmaxf(M, dsm[(w * H + hh) * DEC_REC]);
     float Ls = 0.f, a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) {
-      const float* rec = dsm + (w * H + head) * DEC_REC;
+    for (int w = 0; w < KS; ++w) {
+      const float* rec = dsm + (w * H + hh) * DEC_REC;
       const float sc = (rec[0] == -INFINITY) ? 0.f : __expf(rec[0] - M);
       Ls += rec[1] * sc;
       a0 += rec[2 + d] * sc;
       a1 += rec[66 + d];
     }
-    float* o = out + head * DEC_REC;
+    float* o = out + hh * DEC_REC;
     if (d == 0) {
       o[0] = M;
       o[1] = Ls;
@@ -209,22 +203,26 @@ int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const 
   if (!workspace || workspace_bytes < need)
     return fail(DFD_ERR_WORKSPACE, "decoder_attention: workspace %zu < %zu bytes", workspace_bytes, need);
   float* part = static_cast<float*>(workspace);
-  const size_t smem = static_cast<size_t>(DEC_WARPS) * H * DEC_REC * sizeof(float);
   const unsigned grid = static_cast<unsigned>(B) * T;
   const __nv_bfloat16* kb = static_cast<const __nv_bfloat16*>(k);
   const __nv_bfloat16* vb = static_cast<const __nv_bfloat16*>(v);
-#define DFD_LAUNCH_DEC(NCH)                                                                                        \
-  do {                                                                                                             \
-    DFD_CUDA_OK(cudaFuncSetAttribute(dec_attn_partial_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                     (int)smem));                                                                  \
-    dec_attn_partial_kernel<NCH><<<grid, DEC_WARPS * 32, smem, stream>>>(qs, kb, vb, stride_b, stride_t, stride_p, \
-                                                                         pos_emb, mask, T, P, part);               \
+#define DFD_LAUNCH_DEC(HH, KSV)                                                                                   \
+  do {                                                                                                            \
+    const size_t smem = static_cast<size_t>(KSV) * HH * DEC_REC * sizeof(float);                                  \
+    static bool configured = false;                                                                               \
+    if (!configured) {                                                                                            \
+      DFD_CUDA_OK(cudaFuncSetAttribute(dec_attn_partial_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                       (int)smem));                                                               \
+      configured = true;                                                                                          \
+    }                                                                                                             \
+    dec_attn_partial_kernel<HH><<<grid, (HH / 4) * KSV * 32, smem, stream>>>(qs, kb, vb, stride_b, stride_t,      \
+                                                                            stride_p, pos_emb, mask, T, P, part); \
   } while (0)
-  switch (H / 4) {
-    case 1: DFD_LAUNCH_DEC(1); break;
-    case 2: DFD_LAUNCH_DEC(2); break;
-    case 3: DFD_LAUNCH_DEC(3); break;
-    default: DFD_LAUNCH_DEC(4); break;
+  switch (H) {
+    case 4: DFD_LAUNCH_DEC(4, 8); break;
+    case 8: DFD_LAUNCH_DEC(8, 4); break;
+    case 12: DFD_LAUNCH_DEC(12, 4); break;
+    default: DFD_LAUNCH_DEC(16, 3); break;
   }
 #undef DFD_LAUNCH_DEC
   DFD_CUDA_OK(cudaGetLastError());
@@ -235,72 +233,133 @@ int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const 
 }
 
 // ------------------------------------------------------------------------------------- small fp32 linear
-// out[b, n] = act( sum_k x[b,k] * W[n,k] + bias[n] ) (+ res[b,n]).  M = B is one token per clip, so these are
-// weights-bandwidth bound: each CTA streams a [16 x K] slab of W once for up to 64 rows of x.
-constexpr int LIN_BM = 64, LIN_BN = 16, LIN_BK = 64, LIN_PAD = 4;
+// out[b, n] = act( sum_k x[b,k] * W[n,k] + bias[n] ) (+ res[b,n]).  M = B is one token per clip, so these layers
+// are weights-bandwidth bound (6.5 M fp32 parameters per block, each read once). To put every SM on the weight
+// stream the K range is split across CTAs: CTA (n-tile of 16 columns, k-split, 64-row b-tile) accumulates a partial
+// [64 x 16] tile with a cp.async double-buffered smem pipeline; partials are reduced in a fixed order by
+// linear_reduce_kernel (deterministic, no atomics), which also applies bias / QuickGELU / residual.
+constexpr int LIN_BM = 64, LIN_BN = 16, LIN_BK = 64, LIN_LD = LIN_BK + 4, LIN_THREADS = 128;
 
-template <bool QGELU>
-__global__ void __launch_bounds__(256)
-linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                  const float* res, float* out, int B, int N, int K) {
-  __shared__ __align__(16) float sx[LIN_BM][LIN_BK + LIN_PAD];
-  __shared__ __align__(16) float sw[LIN_BN][LIN_BK + LIN_PAD];
-  const int n0 = blockIdx.x * LIN_BN, b0 = blockIdx.y * LIN_BM;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx: column, ty: 4 rows
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += LIN_BK) {
-    // x tile: 64 rows x 16 float4
-    for (int i = threadIdx.x; i < LIN_BM * (LIN_BK / 4); i += 256) {
-      const int r = i / (LIN_BK / 4), c = (i % (LIN_BK / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b0 + r < B && k0 + c < K) v = *reinterpret_cast<const float4*>(x + static_cast<int64_t>(b0 + r) * K + k0 + c);
-      *reinterpret_cast<float4*>(&sx[r][c]) = v;
+__device__ __forceinline__ void cp_async_f4(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(LIN_THREADS)
+linear_partial_kernel(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ part, int B, int N,
+                      int K, int k_per_split) {
+  __shared__ __align__(16) float sx[2][LIN_BM][LIN_LD];
+  __shared__ __align__(16) float sw[2][LIN_BN][LIN_LD];
+  const int n0 = blockIdx.x * LIN_BN, b0 = blockIdx.z * LIN_BM;
+  const int kbeg = blockIdx.y * k_per_split, kend = min(K, kbeg + k_per_split);
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;  // tx: 2 columns (tx, tx+8); ty: 4 rows (ty, ty+16, ty+32, ty+48)
+
+  auto load_stage = [&](int stage, int k0) {
+    // x tile: 64 rows x 16 float4 = 1024 float4 -> 8 per thread; W tile: 16 x 16 = 256 -> 2 per thread
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * LIN_THREADS;
+      const int r = idx >> 4, c = (idx & 15) * 4;
+      const bool ok = (b0 + r < B) && (k0 + c < kend);
+      cp_async_f4(&sx[stage][r][c], x + static_cast<int64_t>(ok ? b0 + r : 0) * K + (ok ? k0 + c : 0), ok);
     }
-    {
-      const int r = threadIdx.x / (LIN_BK / 4), c = (threadIdx.x % (LIN_BK / 4)) * 4;  // 16 rows x 16 float4
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + r < N && k0 + c < K) v = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(n0 + r) * K + k0 + c));
-      *reinterpret_cast<float4*>(&sw[r][c]) = v;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * LIN_THREADS;
+      const int r = idx >> 4, c = (idx & 15) * 4;
+      const bool ok = (n0 + r < N) && (k0 + c < kend);
+      cp_async_f4(&sw[stage][r][c], W + static_cast<int64_t>(ok ? n0 + r : 0) * K + (ok ? k0 + c : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[4][2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = 0.f;
+  const int nsteps = (kend - kbeg + LIN_BK - 1) / LIN_BK;
+  if (nsteps > 0) load_stage(0, kbeg);
+  for (int s = 0; s < nsteps; ++s) {
+    if (s + 1 < nsteps) {
+      load_stage((s + 1) & 1, kbeg + (s + 1) * LIN_BK);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const int st = s & 1;
 #pragma unroll
     for (int k = 0; k < LIN_BK; k += 4) {
-      const float4 w = *reinterpret_cast<const float4*>(&sw[tx][k]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&sw[st][tx][k]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&sw[st][tx + 8][k]);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(&sx[ty * 4 + r][k]);
-        acc[r] = fmaf(xv.x, w.x, acc[r]);
-        acc[r] = fmaf(xv.y, w.y, acc[r]);
-        acc[r] = fmaf(xv.z, w.z, acc[r]);
-        acc[r] = fmaf(xv.w, w.w, acc[r]);
+        const float4 xv = *reinterpret_cast<const float4*>(&sx[st][ty + 16 * r][k]);
+        acc[r][0] = fmaf(xv.x, w0.x, acc[r][0]);
+        acc[r][0] = fmaf(xv.y, w0.y, acc[r][0]);
+        acc[r][0] = fmaf(xv.z, w0.z, acc[r][0]);
+        acc[r][0] = fmaf(xv.w, w0.w, acc[r][0]);
+        acc[r][1] = fmaf(xv.x, w1.x, acc[r][1]);
+        acc[r][1] = fmaf(xv.y, w1.y, acc[r][1]);
+        acc[r][1] = fmaf(xv.z, w1.z, acc[r][1]);
+        acc[r][1] = fmaf(xv.w, w1.w, acc[r][1]);
       }
     }
     __syncthreads();
   }
-  const int n = n0 + tx;
-  if (n < N) {
-    const float bn = bias ? bias[n] : 0.f;
+  float* dst = part + static_cast<int64_t>(blockIdx.y) * B * N;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int b = b0 + ty * 4 + r;
-      if (b < B) {
-        float v = acc[r] + bn;
-        if (QGELU) v = v / (1.f + __expf(-1.702f * v));
-        if (res) v += res[static_cast<int64_t>(b) * N + n];
-        out[static_cast<int64_t>(b) * N + n] = v;
-      }
+  for (int r = 0; r < 4; ++r) {
+    const int b = b0 + ty + 16 * r;
+    if (b < B) {
+      if (n0 + tx < N) dst[static_cast<int64_t>(b) * N + n0 + tx] = acc[r][0];
+      if (n0 + tx + 8 < N) dst[static_cast<int64_t>(b) * N + n0 + tx + 8] = acc[r][1];
     }
   }
 }
 
-int linear_f32(const float* x, const float* W, const float* bias, const float* res, float* out, int B, int N, int K,
-               bool qgelu, cudaStream_t stream) {
+template <bool QGELU>
+__global__ void linear_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
+                                     const float* res, float* out, int B, int N) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(B) * N;
+  if (i >= total) return;
+  float v = bias ? bias[i % N] : 0.f;
+  for (int s = 0; s < splits; ++s) v += part[s * total + i];
+  if (QGELU) v = v / (1.f + __expf(-1.702f * v));
+  if (res) v += res[i];
+  out[i] = v;
+}
+
+constexpr int LIN_MAX_SPLITS = 8;
+
+size_t linear_workspace_bytes(int B, int max_n) {
+  return static_cast<size_t>(LIN_MAX_SPLITS) * B * max_n * sizeof(float);
+}
+
+int linear_f32(const dfd_ctx* ctx, const float* x, const float* W, const float* bias, const float* res, float* out,
+               int B, int N, int K, bool qgelu, float* part, cudaStream_t stream) {
   DFD_CHECK_ARG(K % 4 == 0, "linear_f32: K=%d must be a multiple of 4", K);
-  dim3 grid((N + LIN_BN - 1) / LIN_BN, (B + LIN_BM - 1) / LIN_BM);
+  const int n_tiles = (N + LIN_BN - 1) / LIN_BN, b_tiles = (B + LIN_BM - 1) / LIN_BM;
+  // enough k-splits to cover the SMs about twice, each at least one BK step, at most LIN_MAX_SPLITS
+  int splits = (2 * ctx->num_sms + n_tiles * b_tiles - 1) / (n_tiles * b_tiles);
+  const int max_by_k = (K + LIN_BK - 1) / LIN_BK;
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits > LIN_MAX_SPLITS) splits = LIN_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  int k_per_split = (K + splits - 1) / splits;
+  k_per_split = (k_per_split + LIN_BK - 1) / LIN_BK * LIN_BK;
+  splits = (K + k_per_split - 1) / k_per_split;
+  dim3 grid(n_tiles, splits, b_tiles);
+  linear_partial_kernel<<<grid, LIN_THREADS, 0, stream>>>(x, W, part, B, N, K, k_per_split);
+  DFD_CUDA_OK(cudaGetLastError());
+  const int64_t total = static_cast<int64_t>(B) * N;
+  const unsigned rgrid = static_cast<unsigned>((total + 255) / 256);
   if (qgelu)
-    linear_f32_kernel<true><<<grid, 256, 0, stream>>>(x, W, bias, res, out, B, N, K);
+    linear_reduce_kernel<true><<<rgrid, 256, 0, stream>>>(part, splits, bias, res, out, B, N);
   else
-    linear_f32_kernel<false><<<grid, 256, 0, stream>>>(x, W, bias, res, out, B, N, K);
+    linear_reduce_kernel<false><<<rgrid, 256, 0, stream>>>(part, splits, bias, res, out, B, N);
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -359,7 +418,7 @@ int project_logits(const float* feature, const float* proj, int B, int D, int O,
 
 // ------------------------------------------------------------------------------------- whole decoder
 struct DecWs {
-  float *x, *y, *qs, *mix, *hid, *part;
+  float *x, *y, *qs, *mix, *hid, *part, *lin;
   size_t total;
 };
 
@@ -379,6 +438,7 @@ static DecWs carve_decoder_ws(void* base, int B, int T, int D, int H) {
   w.mix = take(sizeof(float) * B * D);
   w.hid = take(sizeof(float) * B * 4 * D);
   w.part = take(dec_attn_workspace_bytes(B, T, H));
+  w.lin = take(linear_workspace_bytes(B, 4 * D));
   w.total = off;
   return w;
 }
@@ -409,21 +469,22 @@ int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_de
     // x = x + out_proj(attn(in_proj(ln_1(x)), K_i, V_i, m))        (models.py:173-174, 136-146)
     DFD_TIMED(DFD_TAG_DEC_OTHER,
               layernorm(ws.x, w->ln_1_weight[i], w->ln_1_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ws.y, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, ws.qs, B, 2 * D,
-                                             D, false, stream));
+    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.y, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, ws.qs, B,
+                                             2 * D, D, false, ws.lin, stream));
     DFD_TIMED(DFD_TAG_DEC_ATTN,
               decoder_attention(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
                                 w->positional_embedding, mask, B, T, P, H, ws.mix, ws.part,
                                 dec_attn_workspace_bytes(B, T, H), stream));
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ws.mix, w->out_proj_weight[i], w->out_proj_bias[i], ws.x, ws.x, B, D, D,
-                                             false, stream));
+    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.mix, w->out_proj_weight[i], w->out_proj_bias[i], ws.x, ws.x, B,
+                                             D, D, false, ws.lin, stream));
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                     (models.py:175)
     DFD_TIMED(DFD_TAG_DEC_OTHER,
               layernorm(ws.x, w->ln_2_weight[i], w->ln_2_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
     DFD_TIMED(DFD_TAG_DEC_LINEAR,
-              linear_f32(ws.y, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, ws.hid, B, 4 * D, D, true, stream));
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ws.hid, w->c_proj_weight[i], w->c_proj_bias[i], ws.x, ws.x, B, D, 4 * D,
-                                             false, stream));
+              linear_f32(ctx, ws.y, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, ws.hid, B, 4 * D, D, true, ws.lin,
+                         stream));
+    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.hid, w->c_proj_weight[i], w->c_proj_bias[i], ws.x, ws.x, B, D,
+                                             4 * D, false, ws.lin, stream));
     scatter_block_out_kernel<<<nblk, nthr, 0, stream>>>(ws.x, block_out, B, D, i, n_blocks);
     DFD_CUDA_OK(cudaGetLastError());
   }
