@@ -187,6 +187,7 @@ mha_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
 }
 
 int mha_fwd_tc(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
+int mha_fwd_tc2(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
 
 int mha_fwd(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream) {
   DFD_CHECK_ARG(n_frames >= 0 && L > 0 && H > 0, "mha_fwd: bad shape");
@@ -194,7 +195,9 @@ int mha_fwd(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L,
   if (n_frames == 0) return 0;
   DFD_CHECK_ARG(qkv && mix, "mha_fwd: null pointer");
   // up to 208 tokens per frame (ViT-B/16, B/32): tcgen05 kernel; longer sequences (ViT-L/14: 257): mma.sync kernel
-  if (L <= 208 && (H * 64) % 8 == 0) return mha_fwd_tc(ctx, qkv, mix, n_frames, L, H, stream);
+  // 129..208 tokens (two 128-row query tiles): pipelined two-tile kernel with P in TMEM; up to 128: one-tile kernel
+  if (L > 128 && L <= 208) return mha_fwd_tc2(ctx, qkv, mix, n_frames, L, H, stream);
+  if (L <= 128) return mha_fwd_tc(ctx, qkv, mix, n_frames, L, H, stream);
   const int LP = (L + 15) & ~15;
   const int threads = (LP / 16) * 32;
   const size_t smem = static_cast<size_t>(3) * LP * attn::ROW_BYTES;

@@ -1,0 +1,425 @@
+// tcgen05 encoder self-attention, pipelined two-tile kernel for 128 < L <= 208 tokens per frame (CLIP ViT-B/16:
+// L = 197). Reference: MultiheadAttention.forward, src/clip/model.py:188-195 — softmax_k((q/8).k) v, no mask.
+//
+// Work item = (frame, head); one persistent CTA per SM, 320 threads:
+//   warp 0        TMA producer: Q [256 x 64] (rows >= L zero-filled), K [208 x 64], V [208 x 64] of the item into a
+//                 2-stage smem ring, so the loads of item i+1 overlap all compute of item i.
+//   warp 1        MMA issuer (one thread). Per 128-row query tile X in {A, B}:
+//                   S_X = Q_X K^T        tcgen05.mma M=128 N=208 K=16 x4, operands in smem, fp32 S in TMEM
+//                   O_X = P_X V          tcgen05.mma M=128 N=64  K=16 x13, A = P from TMEM (bf16 pairs written by the
+//                                        softmax warps over the dead S columns), B = V from smem (MN-major)
+//                 issue order PV_A(i), S_A(i+1), PV_B(i), S_B(i+1): the tensor core works for one tile while the
+//                 other tile's warpgroup is in its softmax.
+//   warps 2..5    softmax + epilogue warpgroup of tile A (thread = query row), warps 6..9 the same for tile B:
+//                 pass 1 row max out of TMEM, pass 2 exp2 / row sum / bf16 P back into TMEM (tcgen05.st), then
+//                 O: tcgen05.ld, 1/rowsum, bf16, swizzled smem staging, TMA store (rows >= L clipped by the map).
+// TMEM (512 columns): tile X owns columns [256 X, 256 X + 208): S fp32 [0,208); P bf16x2 [0,104) once S is consumed;
+// O fp32 [128,192) (S columns that pass 2 has already read).
+#include "common.cuh"
+#include "host_common.h"
+#include <stdlib.h>
+
+namespace dfd {
+
+namespace attn2 {
+constexpr int QT = 128;
+constexpr int KP = 208;
+constexpr int DH = 64;
+constexpr int THREADS = 320;
+constexpr int Q_BYTES = 2 * QT * 128;   // 32 KB
+constexpr int KV_BYTES = KP * 128;      // 26 KB
+constexpr int STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;
+constexpr int Q_OFF = 0, K_OFF = Q_BYTES, V_OFF = Q_BYTES + KV_BYTES;
+constexpr int O_OFF = 2 * STAGE_BYTES;  // 8 warps x 4 KB output staging
+constexpr int O_BYTES = 8 * 4096;
+constexpr int BAR_OFF = O_OFF + O_BYTES;
+// barriers: load_full[2], stage_empty[2], s_full[2], p_full[2], o_full[2], o_empty[2]
+constexpr int NUM_BARS = 12;
+constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
+constexpr int SMEM_BYTES = TMEM_PTR_OFF + 16 + 1024;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TILE_COLS = 256;
+constexpr uint32_t O_COL = 128;
+constexpr uint32_t LOAD_BYTES = STAGE_BYTES;
+constexpr int NCHUNK = 7;  // 6 x 32 + 16 key columns
+static_assert(STAGE_BYTES % 1024 == 0 && KV_BYTES % 1024 == 0, "tiles must stay 1024-byte aligned");
+}  // namespace attn2
+
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x (K/2) 32-bit columns of packed bf16 pairs.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: this warp's 32 lanes x 16 consecutive 32-bit columns (one row per thread).
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0],"
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0],"
+      "{%1, %2, %3, %4, %5, %6, %7, %8};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// chunk c of the S row: 32 fp32 columns (c < 6) or 16 (c == 6) into r[0..)
+__device__ __forceinline__ void ld_chunk(uint32_t t_s, int c, uint32_t (&r)[32]) {
+  if (c < 6) {
+    tmem_ld32(t_s + c * 32, r);
+  } else {
+    uint32_t (&h)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
+    tmem_ld16(t_s + c * 32, h);
+  }
+}
+
+__global__ void __launch_bounds__(attn2::THREADS, 1)
+mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   const __grid_constant__ CUtensorMap tmO, int L, int H, int num_items, int dyn_order) {
+  using namespace attn2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* load_full = bars + 0;
+  uint64_t* stage_empty = bars + 2;
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_empty = bars + 10;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + TMEM_PTR_OFF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * DH;
+  const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&load_full[i], 1);
+        mbar_init(&stage_empty[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_full[i], 128);
+        mbar_init(&o_full[i], 1);
+        mbar_init(&o_empty[i], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < n_my; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int h = item % H, f = item / H;
+        const int st = it & 1;
+        if (it >= 2) mbar_wait(&stage_empty[st], ((it >> 1) & 1) ^ 1);
+        uint8_t* sb = smem + st * STAGE_BYTES;
+        mbar_arrive_expect_tx(&load_full[st], LOAD_BYTES);
+        tma_load_3d(&tmQ, &load_full[st], sb + Q_OFF, h * DH, 0, f, kEvictFirst);
+        tma_load_3d(&tmKV, &load_full[st], sb + K_OFF, D + h * DH, 0, f, kEvictFirst);
+        tma_load_3d(&tmKV, &load_full[st], sb + V_OFF, 2 * D + h * DH, 0, f, kEvictFirst);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && n_my > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KP);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(QT, DH, /*b_mn_major=*/true);
+      auto issue_s = [&](int x, int st) {
+        const uint8_t* sb = smem + st * STAGE_BYTES;
+        const uint64_t q_desc = umma_desc_sw128(sb + Q_OFF + x * (QT * 128));
+        const uint64_t k_desc = umma_desc_sw128(sb + K_OFF);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + x * TILE_COLS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x, int st) {
+        const uint8_t* sb = smem + st * STAGE_BYTES;
+        const uint64_t v_desc = umma_desc_sw128_mn(sb + V_OFF);
+        const uint32_t t_tile = tmem_base + x * TILE_COLS;
+#pragma unroll
+        for (int kk = 0; kk < KP / 16; ++kk)
+          umma_bf16_ts(t_tile + O_COL, t_tile + kk * 8, v_desc + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_o,
+                       kk != 0);
+        umma_commit(&o_full[x]);
+      };
+      // Dynamic issue order: each tile X alternates PV_X(it) [needs P of item it] and S_X(it+1) [needs the next
+      // stage loaded and O_X(it) drained]; the thread polls both tiles and serves whichever is ready, so the tensor
+      // core works for one tile while the other tile's warpgroup is in its softmax, in whatever phase they settle.
+      mbar_wait(&load_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      if (!(dyn_order & 1)) {
+        for (int it = 0; it < n_my; ++it) {
+          const int st = it & 1;
+          const uint32_t ph = it & 1;
+          const bool nxt = it + 1 < n_my;
+          const int nst = (it + 1) & 1;
+          mbar_wait(&p_full[0], ph);
+          tc_fence_after();
+          issue_pv(0, st);
+          if (nxt) {
+            mbar_wait(&load_full[nst], ((it + 1) >> 1) & 1);
+            mbar_wait(&o_empty[0], ph);
+            tc_fence_after();
+            issue_s(0, nst);
+          }
+          mbar_wait(&p_full[1], ph);
+          tc_fence_after();
+          issue_pv(1, st);
+          umma_commit(&stage_empty[st]);
+          if (nxt) {
+            mbar_wait(&o_empty[1], ph);
+            tc_fence_after();
+            issue_s(1, nst);
+          }
+        }
+      } else {
+      int it_x[2] = {0, 0};        // item whose PV (state 0) or whose successor's S (state 1) is pending
+        int state[2] = {0, 0};
+        int pv_issued[2] = {0, 0};   // per stage parity: number of tiles whose PV of the current item was issued
+        int remaining = 2;
+        uint32_t spins = 0;
+        while (remaining > 0) {
+          bool progressed = false;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (state[x] == 2) continue;
+            const int it = it_x[x];
+            const uint32_t ph = it & 1;
+            if (state[x] == 0) {
+              if (!mbar_try_wait(&p_full[x], ph)) continue;
+              tc_fence_after();
+              const int st = it & 1;
+              issue_pv(x, st);
+              if (++pv_issued[st] == 2) {
+                pv_issued[st] = 0;
+                umma_commit(&stage_empty[st]);  // every MMA reading this stage's Q/K/V has been issued before this
+              }
+              if (it + 1 < n_my) {
+                state[x] = 1;
+              } else {
+                state[x] = 2;
+                --remaining;
+              }
+              progressed = true;
+            } else {
+              const int nst = (it + 1) & 1;
+              if (!mbar_try_wait(&load_full[nst], ((it + 1) >> 1) & 1)) continue;
+              if (!mbar_try_wait(&o_empty[x], ph)) continue;
+              tc_fence_after();
+              issue_s(x, nst);
+              it_x[x] = it + 1;
+              state[x] = 0;
+              progressed = true;
+            }
+          }
+          if (progressed) {
+            spins = 0;
+          } else if (++spins > DFD_SPIN_LIMIT) {
+            printf("dfd: mha_fwd_tc2 MMA scheduler timed out (block %d)\n", (int)blockIdx.x);
+            __trap();
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------ softmax + epilogue warps
+    const int x = (warp - 2) >> 2;         // query tile of this warpgroup
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int row0 = x * QT + q * 32;      // first query row of this warp inside the frame
+    const bool warp_active = row0 < L;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + x * TILE_COLS;
+    uint8_t* obuf = smem + O_OFF + (warp - 2) * 4096;
+    const float sc = 0.125f * 1.4426950408889634f;
+    int h = static_cast<int>(blockIdx.x) % H, f = static_cast<int>(blockIdx.x) / H;
+    const int dh_step = static_cast<int>(gridDim.x) % H, df_step = static_cast<int>(gridDim.x) / H;
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t ph = it & 1;
+      mbar_wait(&s_full[x], ph);
+      tc_fence_after();
+      float inv_sum = 0.f;
+      if (warp_active) {
+        uint32_t ra[32], rb[32];
+        // ---- pass 1: row max over the L real keys (chunk c+1 is in flight while chunk c is reduced)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (dyn_order & 2) mx0 = 20.f;
+        if (!(dyn_order & 2)) ld_chunk(t_row, 0, ra);
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          if (dyn_order & 2) break;
+          uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+          uint32_t (&nx)[32] = (c & 1) ? ra : rb;
+          tmem_ld_wait();
+          if (c + 1 < NCHUNK) ld_chunk(t_row, c + 1, nx);
+          const int c0 = c * 32, w = (c < 6) ? 32 : 16;
+          if (c < 4 || c0 + w <= L) {  // this kernel runs for L > 128: chunks 0..3 are always complete
+#pragma unroll
+            for (int j = 0; j < w; j += 4) {
+              mx0 = max3(mx0, __uint_as_float(cur[j]), __uint_as_float(cur[j + 1]));
+              mx1 = max3(mx1, __uint_as_float(cur[j + 2]), __uint_as_float(cur[j + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < w; ++j)
+              if (c0 + j < L) mx0 = fmaxf(mx0, __uint_as_float(cur[j]));
+          }
+        }
+        const float mo = fmaxf(mx0, mx1) * sc;
+        // ---- pass 2: p = exp2(s*sc - max*sc), row sum, bf16 pairs back into TMEM columns [16c, 16c+16).
+        // Software pipelined: the exp2 of chunk c are issued (MUFU) before the sums / packing / tcgen05.st of
+        // chunk c-1, so the MUFU pipe always has independent work queued behind it.
+        float sum0 = 0.f, sum1 = 0.f;
+        float ea[32], eb[32];
+        ld_chunk(t_row, 0, ra);
+#pragma unroll
+        for (int c = 0; c <= NCHUNK; ++c) {
+          if (c < NCHUNK) {
+            uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+            uint32_t (&nx)[32] = (c & 1) ? ra : rb;
+            float (&e)[32] = (c & 1) ? eb : ea;
+            tmem_ld_wait();
+            if (c + 1 < NCHUNK) ld_chunk(t_row, c + 1, nx);
+            const int c0 = c * 32, w = (c < 6) ? 32 : 16;
+            if (c < 4 || c0 + w <= L) {
+#pragma unroll
+              for (int j = 0; j < w; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(cur[j]), sc, -mo));
+            } else {
+#pragma unroll
+              for (int j = 0; j < w; ++j)
+                e[j] = (c0 + j < L) ? fast_exp2(fmaf(__uint_as_float(cur[j]), sc, -mo)) : 0.f;
+            }
+          }
+          if (c > 0) {
+            const int cp = c - 1, wp = (cp < 6) ? 32 : 16;
+            float (&e)[32] = (cp & 1) ? eb : ea;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < wp; j += 2) {
+              sum0 += e[j];
+              sum1 += e[j + 1];
+              pk[j >> 1] = pack_bf16(e[j], e[j + 1]);
+            }
+            if (cp < 6)
+              tmem_st16(t_row + cp * 16, pk);
+            else
+              tmem_st8(t_row + cp * 16, pk);
+          }
+        }
+        tmem_st_wait();
+        inv_sum = 1.f / (sum0 + sum1);
+      }
+      // P is in TMEM, S fully consumed: hand the tile to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&p_full[x]);
+
+      mbar_wait(&o_full[x], ph);
+      tc_fence_after();
+      if (warp_active) {
+        uint32_t o0[32], o1[32];
+        tmem_ld32(t_row + O_COL, o0);
+        tmem_ld32(t_row + O_COL + 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&o_empty[x]);
+        if (lane == 0) tma_store_wait_read<0>();  // previous store out of this warp's staging buffer is done
+        __syncwarp();
+        uint8_t* dst = obuf + lane * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t* src = (ch < 4) ? (o0 + ch * 8) : (o1 + (ch - 4) * 8);
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(src[0]) * inv_sum, __uint_as_float(src[1]) * inv_sum);
+          v.y = pack_bf16(__uint_as_float(src[2]) * inv_sum, __uint_as_float(src[3]) * inv_sum);
+          v.z = pack_bf16(__uint_as_float(src[4]) * inv_sum, __uint_as_float(src[5]) * inv_sum);
+          v.w = pack_bf16(__uint_as_float(src[6]) * inv_sum, __uint_as_float(src[7]) * inv_sum);
+          *reinterpret_cast<uint4*>(dst + ((ch ^ (lane & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, obuf, h * DH, row0, f);
+          tma_store_commit();
+        }
+      } else {
+        tc_fence_before();
+        mbar_arrive(&o_empty[x]);
+      }
+      h += dh_step;
+      f += df_step;
+      if (h >= H) {
+        h -= H;
+        ++f;
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int mha_fwd_tc2(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream) {
+  using namespace attn2;
+  DFD_CHECK_ARG(L > QT && L <= KP, "mha_fwd_tc2: needs 128 < L <= 208, got %d", L);
+  const int D = H * DH;
+  CUtensorMap tmQ, tmKV, tmO;
+  const uint64_t frame_ld = static_cast<uint64_t>(L) * 3 * D;
+  DFD_TRY(make_tmap_3d(ctx, &tmQ, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_frames, L, 3 * D, 3 * D, frame_ld, 2 * QT, DH));
+  DFD_TRY(make_tmap_3d(ctx, &tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_frames, L, 3 * D, 3 * D, frame_ld, KP, DH));
+  DFD_TRY(make_tmap_3d(ctx, &tmO, mix, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_frames, L, D, D,
+                       static_cast<uint64_t>(L) * D, 32, DH));
+  static bool configured[64] = {};
+  if (!configured[ctx->device & 63]) {
+    DFD_CUDA_OK(cudaFuncSetAttribute(mha_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured[ctx->device & 63] = true;
+  }
+  const int num_items = n_frames * H;
+  const int grid = num_items < ctx->num_sms ? num_items : ctx->num_sms;
+  static const int dyn_order = []() {
+    const char* e = getenv("DFD_MHA_ORDER");
+    return e ? atoi(e) : 0;
+  }();
+  mha_fwd_tc2_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, L, H, num_items, dyn_order);
+  DFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dfd

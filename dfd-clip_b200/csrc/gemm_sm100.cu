@@ -13,6 +13,7 @@
 // Reference ops replaced: F.linear / nn.Linear / nn.Conv2d in src/clip/model.py:186,197,209,211,277.
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
 
 namespace dfd {
 
@@ -228,6 +229,287 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// =====================================================================================================
+// 2-SM variant (tcgen05 cta_group::2): a cluster of two CTAs (one SM pair) computes a 256 x 256 tile.
+// Each CTA loads its own 128 rows of A and its own 128-row half of the W tile (32 KB per stage instead of
+// 48 KB: one third less L2->SM traffic and one third less shared-memory read traffic per FLOP), the leader
+// CTA's MMA thread issues tcgen05.mma.cta_group::2 (M=256, N=256, K=16) which reads both CTAs' shared
+// memory and writes rows [0,128) of the accumulator to the leader's TMEM and rows [128,256) to the peer's.
+// Each CTA drains its own TMEM with the same epilogue as the 1-SM kernel.
+// Cross-CTA signalling: TMA loads of both CTAs complete_tx on the LEADER's full barrier; tcgen05.commit
+// multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps
+// arrive remotely on the leader's "accumulator drained" barrier.
+namespace gemm2 {
+constexpr int BM = 128;            // rows per CTA (256 per cluster)
+constexpr int BN = 256;
+constexpr int BNH = 128;           // W rows loaded by each CTA
+constexpr int BK = 64;
+constexpr int STAGES = 5;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE = BNH * BK * 2;  // 16 KB
+constexpr int OUT_BUF = 32 * 128;
+constexpr int OUT_BUFS_PER_WARP = 2;
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each draining one 128-column half of the tile
+constexpr int THREADS = 32 * (2 + EPI_WARPS);
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
+constexpr int OFF_OUT = OFF_B + STAGES * B_STAGE;
+constexpr int OFF_BAR = OFF_OUT + EPI_WARPS * OUT_BUFS_PER_WARP * OUT_BUF;
+constexpr int NUM_BARS = 2 * STAGES + 4;
+constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+constexpr uint32_t TMEM_COLS = 512;
+}  // namespace gemm2
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                int c1, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2::THREADS, 1)
+gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+  using namespace gemm2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int num_m2 = (M + 2 * BM - 1) / (2 * BM);
+  const int num_n = N / BN;
+  const int num_tiles = num_m2 * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full[a], 1);
+        mbar_init(&tmem_empty[a], 2 * EPI_WARPS);  // one elected arrival per epilogue warp of both CTAs
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int a_row = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+        const int b_row = n_blk * BN + static_cast<int>(rank) * BNH;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE + B_STAGE));
+          const uint32_t bar = mapa_u32(&full_bar[stage], 0);
+          tma_load_2d_2sm(&tmA, bar, smem + OFF_A + stage * A_STAGE, kb * BK, a_row, kEvictNormal);
+          tma_load_2d_2sm(&tmB, bar, smem + OFF_B + stage * B_STAGE, kb * BK, b_row, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem + OFF_A + stage * A_STAGE);
+          const uint64_t b_desc = umma_desc_sw128(smem + OFF_B + stage * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);  // both CTAs' stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);  // accumulator complete in both CTAs' TMEM
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs)
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    uint8_t* obuf = smem + OFF_OUT + ew * (OUT_BUFS_PER_WARP * OUT_BUF);
+    constexpr bool kOutF32 = (EPI == DFD_EPI_STORE_F32 || EPI == DFD_EPI_ADD_F32);
+    constexpr int COLS_PER_BOX = kOutF32 ? 32 : 64;
+    constexpr int NUM_BOX = BN / COLS_PER_BOX;
+    constexpr int BOX_PER_WARP = NUM_BOX / 2;
+    const int box_begin = (ew >> 2) * BOX_PER_WARP;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + q * 32;
+      const int col0 = n_blk * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int box = box_begin; box < box_begin + BOX_PER_WARP; ++box) {
+        const int c = col0 + box * COLS_PER_BOX;
+        uint32_t packed[32];
+        if constexpr (kOutF32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + box * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c + j)) : make_float4(0, 0, 0, 0);
+            packed[j + 0] = __float_as_uint(__uint_as_float(r[j + 0]) + b4.x);
+            packed[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
+            packed[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
+            packed[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld32(t_row + box * 64 + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 =
+                  bias ? __ldg(reinterpret_cast<const float4*>(bias + c + half * 32 + j)) : make_float4(0, 0, 0, 0);
+              float v0 = __uint_as_float(r[j + 0]) + b4.x;
+              float v1 = __uint_as_float(r[j + 1]) + b4.y;
+              float v2 = __uint_as_float(r[j + 2]) + b4.z;
+              float v3 = __uint_as_float(r[j + 3]) + b4.w;
+              if constexpr (EPI == DFD_EPI_STORE_BF16_QGELU) {
+                v0 = quick_gelu_fast(v0);
+                v1 = quick_gelu_fast(v1);
+                v2 = quick_gelu_fast(v2);
+                v3 = quick_gelu_fast(v3);
+              }
+              packed[half * 16 + j / 2 + 0] = pack_bf16(v0, v1);
+              packed[half * 16 + j / 2 + 1] = pack_bf16(v2, v3);
+            }
+          }
+        }
+        if (box == box_begin + BOX_PER_WARP - 1) {
+          // all TMEM reads of this accumulator are done in this warp: tell the leader's MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+        }
+        if (lane == 0) tma_store_wait_read<OUT_BUFS_PER_WARP - 1>();
+        __syncwarp();
+        uint8_t* dst = obuf + buf * OUT_BUF + lane * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 v = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(dst + ((ch ^ (lane & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          if constexpr (EPI == DFD_EPI_ADD_F32)
+            tma_reduce_add_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
+          else
+            tma_store_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
+        }
+        if (lane == 0) tma_store_commit();
+        buf ^= 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  // no CTA of the pair may exit (or free TMEM) while the other can still signal it or read its shared memory
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
 // --------------------------------------------------------------------------------------------- host side
 template <int EPI>
 static int launch(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
@@ -243,6 +525,33 @@ static int launch(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap&
   gemm_bf16_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, bias, M, N, K);
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int EPI>
+static int launch2(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                   const float* bias, int M, int N, int K, cudaStream_t stream) {
+  using namespace gemm2;
+  static bool configured[64] = {};
+  if (!configured[ctx->device & 63]) {
+    DFD_CUDA_OK(
+        cudaFuncSetAttribute(gemm_bf16_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured[ctx->device & 63] = true;
+  }
+  const int num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
+  const int max_clusters = ctx->num_sms / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  gemm_bf16_2sm_kernel<EPI><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  DFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// DFD_GEMM_2SM=0 selects the 1-SM kernel (A/B comparisons); default: SM-pair kernel whenever there are >= 2 row blocks.
+static bool use_2sm(int M) {
+  static const int mode = []() {
+    const char* e = getenv("DFD_GEMM_2SM");
+    return e ? atoi(e) : 1;
+  }();
+  return mode != 0 && M > gemm::BM;
 }
 
 int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
@@ -261,12 +570,27 @@ int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int
 
   CUtensorMap tmA, tmB, tmC;
   DFD_TRY(make_tmap_2d(ctx, &tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK));
-  DFD_TRY(make_tmap_2d(ctx, &tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, BN, BK));
+  const bool two_sm = use_2sm(M);
+  DFD_TRY(make_tmap_2d(ctx, &tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, two_sm ? gemm2::BNH : BN, BK));
   if (f32)
     DFD_TRY(make_tmap_2d(ctx, &tmC, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldo, 32, 32));
   else
     DFD_TRY(make_tmap_2d(ctx, &tmC, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldo, 32, 64));
 
+  if (two_sm) {
+    switch (epilogue) {
+      case DFD_EPI_STORE_BF16:
+        return launch2<DFD_EPI_STORE_BF16>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+      case DFD_EPI_STORE_BF16_QGELU:
+        return launch2<DFD_EPI_STORE_BF16_QGELU>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+      case DFD_EPI_STORE_F32:
+        return launch2<DFD_EPI_STORE_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+      case DFD_EPI_ADD_F32:
+        return launch2<DFD_EPI_ADD_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+      default:
+        return fail(DFD_ERR_INVALID, "gemm: unknown epilogue %d", epilogue);
+    }
+  }
   switch (epilogue) {
     case DFD_EPI_STORE_BF16:
       return launch<DFD_EPI_STORE_BF16>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);

@@ -118,7 +118,8 @@ def test_patchify(cuda_device, r, patch):
     assert torch.equal(got[:, 1:, :k], ref.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("n_frames,seq,heads", [(2, 197, 12), (3, 257, 16), (1, 16, 4), (2, 50, 12)])
+@pytest.mark.parametrize("n_frames,seq,heads", [(2, 197, 12), (3, 257, 16), (1, 16, 4), (2, 50, 12), (40, 197, 12),
+                                                (30, 129, 8), (26, 208, 12), (64, 160, 4), (2, 128, 12)])
 def test_mha_fwd(cuda_device, n_frames, seq, heads):
     nat = _native()
     d = heads * 64
