@@ -15,7 +15,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libdfdclip_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-NVCC_FLAGS = [
+NVCC_FLAGS = (["-DDFD_MHA_TRACE"] if os.environ.get("DFD_MHA_TRACE") else []) + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -39,9 +39,12 @@ int make_tmap_2d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtenso
 
 int make_tmap_3d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
                  uint64_t frames, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t frame_ld, uint32_t box_rows,
-                 uint32_t box_cols) {
+                 uint32_t box_cols, bool swizzle128) {
   if (!ctx || !ctx->encode_tiled) return fail(DFD_ERR_INVALID, "tensor map: context has no driver entry point");
-  if (box_cols * elem_bytes != 128) return fail(DFD_ERR_INVALID, "tensor map: box inner extent must be 128 bytes");
+  if (swizzle128 && box_cols * elem_bytes != 128)
+    return fail(DFD_ERR_INVALID, "tensor map: box inner extent must be 128 bytes");
+  if (!swizzle128 && (box_cols * elem_bytes) % 16 != 0)
+    return fail(DFD_ERR_INVALID, "tensor map: box inner extent must be a multiple of 16 bytes");
   if ((ld * elem_bytes) % 16 != 0 || (frame_ld * elem_bytes) % 16 != 0)
     return fail(DFD_ERR_INVALID, "tensor map: pitches must be multiples of 16 bytes");
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail(DFD_ERR_INVALID, "tensor map: base must be 16-byte aligned");
@@ -52,7 +55,8 @@ int make_tmap_3d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtenso
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode(out, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DFD_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed with CUresult %d", (int)r);
   return 0;

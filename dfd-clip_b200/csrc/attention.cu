@@ -5,6 +5,7 @@
 // Tensor work is issued with mma.sync (bf16, fp32 accumulate).
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
 
 namespace dfd {
 

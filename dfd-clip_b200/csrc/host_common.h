@@ -79,7 +79,7 @@ int make_tmap_2d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtenso
 // zero-filled on load, clipped on store), row pitch `ld` elements, frame pitch `frame_ld` elements.
 int make_tmap_3d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
                  uint64_t frames, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t frame_ld, uint32_t box_rows,
-                 uint32_t box_cols);
+                 uint32_t box_cols, bool swizzle128 = true);
 
 // RAII event pair around one kernel launch (no-op unless timing is enabled on the context).
 struct ScopedTimer {
