@@ -171,8 +171,12 @@ class VisionTransformer(nn.Module):
             self._workspace = ws
         return ws
 
-    def encode(self, x, keep_layers=None, need_out=False, last_qkv_only=None):
-        """Run the encoder on frames x[N,3,R,R] (fp32, cuda). Returns ``(qkv, outs)``: ``qkv[l]`` is the packed
+    def encode(self, x, keep_layers=None, need_out=False, last_qkv_only=None, qkv_into=None, frame_offset=0):
+        """``qkv_into`` (optional): dict layer -> preallocated bf16 ``[N_total*L, 3D]`` buffer; the rows of these
+        ``N`` frames are written at frame ``frame_offset`` (lets a caller encode a batch chunk by chunk into one set
+        of tap buffers and run the decoder once).
+
+        Run the encoder on frames x[N,3,R,R] (fp32, cuda). Returns ``(qkv, outs)``: ``qkv[l]`` is the packed
         bf16 ``[N*L, 3D]`` buffer of layer l for every l in ``keep_layers`` (default: all layers), ``outs[l]`` the
         fp32 residual stream after layer l when ``need_out``. Layers after the last kept one are not executed, and
         the last kept layer stops after its QKV projection unless ``need_out`` (dead-work skipping)."""
@@ -198,7 +202,17 @@ class VisionTransformer(nn.Module):
             qkv_only = True if last_qkv_only is None else bool(last_qkv_only)
         packed = self._packed_weights()
         dims = self._dims()
-        qkv = {l: torch.empty((n * seq, 3 * d), dtype=torch.bfloat16, device=dev) for l in keep}
+        if qkv_into is None:
+            qkv = {l: torch.empty((n * seq, 3 * d), dtype=torch.bfloat16, device=dev) for l in keep}
+        else:
+            qkv = {}
+            for l in keep:
+                buf = qkv_into[l]
+                if buf.dtype != torch.bfloat16 or buf.dim() != 2 or buf.shape[1] != 3 * d or not buf.is_contiguous() \
+                        or buf.device != dev or buf.shape[0] < (frame_offset + n) * seq:
+                    raise ValueError("qkv_into[%d] must be a contiguous bf16 [>=%d, %d] buffer on %s" %
+                                     (l, (frame_offset + n) * seq, 3 * d, dev))
+                qkv[l] = buf.narrow(0, frame_offset * seq, n * seq)
         outs = {l: torch.empty((n, seq, d), dtype=torch.float32, device=dev) for l in range(self.layers)} if need_out else {}
         if n == 0:
             return qkv, outs

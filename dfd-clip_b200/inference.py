@@ -1,8 +1,8 @@
 """Video-level scoring driver: the caller loop of the reference's ``inference.py:107-156`` around the hot path.
 
-* ``predict_from_host``: clips in pinned host memory -> logits in host memory, H2D copies double-buffered on a copy
-  stream so they overlap the encoder of the previous chunk (the reference does a blocking ``.to(device)`` /
-  ``.to("cpu")`` per chunk, inference.py:116-118).
+* ``predict_from_host``: clips in pinned host memory -> logits in host memory; the encoder runs chunk by chunk with
+  the H2D copies double-buffered on a copy stream, the decoder once per batch (the reference does a blocking
+  ``.to(device)`` / ``.to("cpu")`` around every chunk, inference.py:116-118).
 * ``shard_videos`` / ``score_videos``: videos are independent units, sharded across ranks by clip count; each rank
   scores its videos (softmax per clip, mean over the clips of a video, inference.py:121,140) and ONE all_gather of
   the per-video scores assembles the result on every rank (the reference gathers once per video, :147-149).
@@ -11,10 +11,33 @@
 import torch
 
 
-class HostClipPipeline:
-    """Reusable double-buffered host->device->host pipeline for ``Detector.predict``."""
+def chunk_schedule(n, chunk_clips=32, first=8, second=24):
+    """Clip counts of the encoder chunks for a batch of n clips: a small first chunk so the GPU starts after a short
+    exposed H2D copy, then growing chunks (each chunk's copy hides behind the previous chunk's encoder)."""
+    sizes, left = [], int(n)
+    for want in (first, second):
+        if left <= 0:
+            break
+        take = min(want, left)
+        sizes.append(take)
+        left -= take
+    while left > 0:
+        take = min(chunk_clips, left)
+        sizes.append(take)
+        left -= take
+    return sizes
 
-    def __init__(self, detector, chunk_clips=16):
+
+class HostClipPipeline:
+    """Host -> device -> host pipeline around the hot path: the ENCODER runs chunk by chunk while the next chunk's
+    frames are copied on a second stream (double-buffered); every chunk writes its K/V taps into one set of
+    whole-batch tap buffers; the DECODER (one query per clip, launch-bound at small batches) then runs ONCE over the
+    whole batch. The reference does a blocking ``.to(device)`` / ``.to("cpu")`` around every chunk's full predict
+    (inference.py:115-118)."""
+
+    MAX_BATCH = 128  # clips per decoder pass (tap buffers: 6 x 930 MB at ViT-B/16, T=8)
+
+    def __init__(self, detector, chunk_clips=32):
         self.det = detector
         self.chunk = int(chunk_clips)
         self.dev = next(detector.decoder.parameters()).device
@@ -22,51 +45,68 @@ class HostClipPipeline:
             raise RuntimeError("HostClipPipeline needs the detector on a CUDA device")
         self.copy_stream = torch.cuda.Stream(self.dev)
         self._bufs = None
+        self._taps = None
 
-    def _buffers(self, x_host, m_host):
-        shape = (self.chunk,) + tuple(x_host.shape[1:])
-        if self._bufs is None or self._bufs[0][0].shape != shape:
-            self._bufs = [(torch.empty(shape, dtype=torch.float32, device=self.dev),
-                           torch.empty((self.chunk, m_host.shape[1]), dtype=torch.bool, device=self.dev))
-                          for _ in range(2)]
+    def _buffers(self, x_host, rows):
+        shape = (rows,) + tuple(x_host.shape[1:])
+        if self._bufs is None or self._bufs[0].shape[1:] != shape[1:] or self._bufs[0].shape[0] < rows:
+            self._bufs = [torch.empty(shape, dtype=torch.float32, device=self.dev) for _ in range(2)]
         return self._bufs
+
+    def _tap_buffers(self, n_frames):
+        enc = self.det.encoder
+        rows, cols = n_frames * enc.tokens_per_frame, 3 * enc.width
+        if self._taps is None or next(iter(self._taps.values())).shape[0] < rows:
+            self._taps = None
+            self._taps = {l: torch.empty((rows, cols), dtype=torch.bfloat16, device=self.dev)
+                          for l in self.det.layer_indices}
+        return self._taps
+
+    def _run_batch(self, x_host, m_host, out_host):
+        n, t = x_host.shape[:2]
+        det, dev, main = self.det, self.dev, torch.cuda.current_stream(self.dev)
+        sizes = chunk_schedule(n, self.chunk)
+        bufs = self._buffers(x_host, max(sizes))
+        taps = self._tap_buffers(n * t)
+        m_dev = m_host.to(dev, non_blocking=True)
+        copied = [torch.cuda.Event() for _ in sizes]
+        consumed = [torch.cuda.Event() for _ in sizes]
+        self.copy_stream.wait_stream(main)
+        s = 0
+        for i, size in enumerate(sizes):
+            xb = bufs[i % 2]
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(consumed[i - 2])  # buffer free again
+                xb[:size].copy_(x_host[s:s + size], non_blocking=True)
+                copied[i].record(self.copy_stream)
+            main.wait_event(copied[i])
+            det.encoder.encode(xb[:size].flatten(0, 1), keep_layers=det.layer_indices, qkv_into=taps,
+                               frame_offset=s * t)
+            consumed[i].record(main)
+            s += size
+        with torch.no_grad():
+            logits, _ = det.predict_from_taps(taps, m_dev, n, t)
+        out_host.copy_(logits[0], non_blocking=True)
 
     def __call__(self, x_host, m_host, out_host=None):
         """x_host fp32 [B,T,3,R,R], m_host bool [B,T] (pinned for real overlap). Returns logits of task 0 on the host
         (fp32 [B, out_dim], pinned); the call returns after the last D2H copy has completed."""
         n = x_host.shape[0]
-        det, dev, main = self.det, self.dev, torch.cuda.current_stream(self.dev)
-        out_dim = det.out_dim[0]
+        out_dim = self.det.out_dim[0]
         if out_host is None:
             out_host = torch.empty((n, out_dim), dtype=torch.float32).pin_memory()
-        if n == 0:
-            return out_host
-        bufs = self._buffers(x_host, m_host)
-        starts = list(range(0, n, self.chunk))
-        copied = [torch.cuda.Event() for _ in starts]
-        consumed = [torch.cuda.Event() for _ in starts]
-        self.copy_stream.wait_stream(main)
-        for i, s in enumerate(starts):
-            e = min(s + self.chunk, n)
-            xb, mb = bufs[i % 2]
-            with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
-                    self.copy_stream.wait_event(consumed[i - 2])  # buffer free again
-                xb[:e - s].copy_(x_host[s:e], non_blocking=True)
-                mb[:e - s].copy_(m_host[s:e], non_blocking=True)
-                copied[i].record(self.copy_stream)
-            main.wait_event(copied[i])
-            logits, _ = det.predict(xb[:e - s], mb[:e - s])
-            consumed[i].record(main)
-            out_host[s:e].copy_(logits[0], non_blocking=True)
-        main.synchronize()
+        for s in range(0, n, self.MAX_BATCH):
+            e = min(s + self.MAX_BATCH, n)
+            self._run_batch(x_host[s:e], m_host[s:e], out_host[s:e])
+        torch.cuda.current_stream(self.dev).synchronize()
         return out_host
 
 
 _PIPELINES = {}
 
 
-def predict_from_host(detector, x_host, m_host, chunk_clips=16):
+def predict_from_host(detector, x_host, m_host, chunk_clips=32):
     """End-to-end public call: host clips in, host logits out (H2D and D2H inside)."""
     key = (id(detector), chunk_clips)
     pipe = _PIPELINES.get(key)

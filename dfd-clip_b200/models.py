@@ -302,14 +302,24 @@ class Detector(nn.Module):
         if with_adapt_features:
             raise Exception("cannot return adaptive features without an adapter")
         b, t = x.shape[:2]
-        seq, h = self.encoder.tokens_per_frame, self.encoder.heads
         with torch.no_grad():
             qkv, _ = self.encoder.encode(x.flatten(0, 1), keep_layers=self.layer_indices)
-            kvs = []
-            for layer in self.layer_indices:
-                view = qkv[layer].view(b, t, seq, 3, h, 64)
-                # discard the CLS token, restore the temporal dimension (:505-507)
-                kvs.append(dict(k=view[:, :, 1:, 1], v=view[:, :, 1:, 2]))
+        return self.predict_from_taps(qkv, m, b, t, with_video_features=with_video_features, train=train)
+
+    def taps_from_qkv(self, qkv, b, t):
+        """Views of the packed per-layer QKV buffers as the decoder's ``[{k, v: [B,T,P,H,64]}]`` list: CLS token
+        discarded, temporal dimension restored (:505-509). No copy."""
+        seq, h = self.encoder.tokens_per_frame, self.encoder.heads
+        kvs = []
+        for layer in self.layer_indices:
+            view = qkv[layer][:b * t * seq].view(b, t, seq, 3, h, 64)
+            kvs.append(dict(k=view[:, :, 1:, 1], v=view[:, :, 1:, 2]))
+        return kvs
+
+    def predict_from_taps(self, qkv, m, b, t, with_video_features=False, train=False):
+        """Second half of ``predict``: decoder + logit normalisation on already-encoded taps (``qkv[layer]`` =
+        packed bf16 ``[B*T*L, 3D]`` buffers from ``encoder.encode``)."""
+        kvs = self.taps_from_qkv(qkv, b, t)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()) and train:
             raise NotImplementedError("the decoder backward (training step) is not implemented yet on the B200 path")
         task_logits, video_features = self.decoder.run(kvs, m, logit_scale=5.0)

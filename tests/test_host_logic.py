@@ -251,3 +251,14 @@ def test_score_videos_two_ranks_gloo_matches_single_process():
             assert p.exitcode == 0
         for r in range(2):
             assert np.array_equal(ret[r], single, equal_nan=True)  # bit-identical on every rank
+
+
+def test_chunk_schedule_covers_batch():
+    from dfdclip_b200.inference import chunk_schedule
+    assert chunk_schedule(64) == [8, 24, 32]
+    assert chunk_schedule(5) == [5]
+    assert chunk_schedule(20) == [8, 12]
+    assert chunk_schedule(100, chunk_clips=16) == [8, 24, 16, 16, 16, 16, 4]
+    assert chunk_schedule(0) == []
+    for n in range(0, 150, 7):
+        assert sum(chunk_schedule(n)) == n and all(c > 0 for c in chunk_schedule(n))

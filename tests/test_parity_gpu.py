@@ -163,3 +163,28 @@ def test_no_cpu_fallback():
     det = Detector(cfg, 4, None).eval()
     with pytest.raises(nat.NativeError):
         det.predict(torch.zeros(1, 4, 3, 32, 32), torch.ones(1, 4, dtype=torch.bool))
+
+
+@pytest.mark.gpu
+def test_predict_from_host_matches_predict(cuda_device):
+    """The chunked-encoder / batched-decoder host pipeline gives bit-identical logits to one predict() call."""
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.inference import HostClipPipeline
+    from dfdclip_b200.models import Detector
+    arch, frames, clips = "small-512x6", 3, 13
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:" + arch
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    det = Detector(cfg, frames, None)
+    sd = synthetic.detector_state_dict(arch, frames, out_dims=(2,), taps=det.layer_indices, seed=0)
+    det.load_state_dict(sd, strict=True)
+    det = det.to(cuda_device).eval()
+    x, m = synthetic.make_clips(clips, frames, synthetic.vit_dims(arch)["image_size"], seed=11)
+    ref = det.predict(x.to(cuda_device), m.to(cuda_device))[0][0].cpu()
+    pipe = HostClipPipeline(det, chunk_clips=4)
+    pipe.MAX_BATCH = 9  # force two decoder passes as well
+    got = pipe(x.pin_memory(), m.pin_memory())
+    assert torch.equal(got, ref)
+    again = pipe(x.pin_memory(), m.pin_memory())
+    assert torch.equal(again, ref)
