@@ -225,7 +225,7 @@ def decoder_attention(qs, k, v, pos_emb, mask):
     assert k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
     m8 = mask.to(torch.uint8).contiguous()
     mix = torch.empty((b, h * 64), dtype=torch.float32, device=k.device)
-    ws = torch.empty((b * t * h * 130,), dtype=torch.float32, device=k.device)
+    ws = torch.empty((2 * b * t * h * 130,), dtype=torch.float32, device=k.device)
     check(load_library().dfd_decoder_attention(
         ctx(k.device), ptr(qs.contiguous()), ptr(k), ptr(v), k.stride(0), k.stride(1), k.stride(2),
         ptr(None if pos_emb is None else pos_emb.contiguous()), ptr(m8), b, t, p, h, ptr(mix), ptr(ws),

@@ -7,10 +7,11 @@
 //   a1 = tanh(q1.K~/8) * 2*sigmoid(-|q1 - K~|_1 / 8)   masked 0               (coda, :117-125)
 //   mix = sum_s 0.5*(a0 + a1) * V~                                            (:142-144)
 // That is one streaming pass over K and V (HBM-bound: 2*S*D*2 bytes per clip and block), done by
-// dec_attn_partial_kernel (one CTA per (clip, frame), online softmax, 8-lane shuffle reductions) and a tiny
-// cross-frame combine. The 1-token-per-clip linear layers are small fp32 GEMMs (weights-bandwidth bound).
+// dec_attn_stream_kernel (decoder_attn_sm100.cu: persistent producer/consumer pipeline over a bulk-copy ring) and a
+// tiny cross-unit combine. The 1-token-per-clip linear layers are small fp32 GEMMs (weights-bandwidth bound).
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
 
 namespace dfd {
 
@@ -37,135 +38,6 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
   return r;
 }
 
-// One CTA per (clip, frame). Warp w handles head group hg = w % (H/4) (4 heads: lane l covers head 4*hg + l/8,
-// channels (l%8)*8 .. +8, i.e. one 16-byte piece of the K row and one of the V row per key) and every KS-th key
-// starting at ks = w / (H/4). A warp-wide load therefore reads 512 contiguous bytes of the token's K (or V) row.
-// Keys are processed UNROLL at a time so that 2*UNROLL independent 16-byte loads per lane are in flight.
-constexpr int DEC_UNROLL = 3;
-
-template <int H>
-__global__ void __launch_bounds__(384, 2)
-dec_attn_partial_kernel(const float* __restrict__ qs, const __nv_bfloat16* __restrict__ kbase,
-                        const __nv_bfloat16* __restrict__ vbase, int64_t stride_b, int64_t stride_t, int64_t stride_p,
-                        const float* __restrict__ pos_emb, const uint8_t* __restrict__ mask, int T, int P,
-                        float* __restrict__ part) {
-  constexpr int HG = H / 4;                      // head groups
-  constexpr int KS = (H == 4) ? 8 : (H == 8 ? 4 : (H == 12 ? 4 : 3));  // key subsets; warps = HG * KS
-  extern __shared__ float dsm[];                 // [KS][H][DEC_REC]
-  const int b = blockIdx.x / T, t = blockIdx.x % T;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* out = part + (static_cast<int64_t>(blockIdx.x) * H) * DEC_REC;
-
-  if (mask[b * T + t] == 0) {
-    // frame absent: neutral element of the combine (m = -inf, l = 0, acc = 0)
-    for (int i = threadIdx.x; i < H * DEC_REC; i += blockDim.x) out[i] = (i % DEC_REC == 0) ? -INFINITY : 0.f;
-    return;
-  }
-  const int hg = warp % HG, ks = warp / HG;
-  const int head = hg * 4 + (lane >> 3), d0 = (lane & 7) * 8;
-
-  float q0[8], q1[8], pe[8], acc0[8], acc1[8];
-  {
-    const float* qh = qs + (static_cast<int64_t>(b) * H + head) * 128;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      q0[e] = qh[d0 + e];
-      q1[e] = qh[64 + d0 + e];
-      pe[e] = pos_emb ? pos_emb[(static_cast<int64_t>(t) * H + head) * 64 + d0 + e] : 0.f;
-      acc0[e] = 0.f;
-      acc1[e] = 0.f;
-    }
-  }
-  float m = -INFINITY, l = 0.f;
-  const int64_t off = b * stride_b + t * stride_t + hg * 256 + lane * 8;
-  const __nv_bfloat16* kf = kbase + off;
-  const __nv_bfloat16* vf = vbase + off;
-
-  for (int p0 = ks; p0 < P; p0 += KS * DEC_UNROLL) {
-    uint4 kraw[DEC_UNROLL], vraw[DEC_UNROLL];
-#pragma unroll
-    for (int u = 0; u < DEC_UNROLL; ++u) {
-      const int p = min(p0 + u * KS, P - 1);
-      kraw[u] = ldg_stream16(kf + p * stride_p);
-      vraw[u] = ldg_stream16(vf + p * stride_p);
-    }
-#pragma unroll
-    for (int u = 0; u < DEC_UNROLL; ++u) {
-      if (p0 + u * KS < P) {
-        float kk[8], vv[8];
-        bf16x8_to_float(kraw[u], kk);
-        bf16x8_to_float(vraw[u], vv);
-        float d0s = 0.f, d1s = 0.f, l1s = 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float kt = kk[e] + pe[e];
-          d0s = fmaf(q0[e], kt, d0s);
-          d1s = fmaf(q1[e], kt, d1s);
-          l1s += fabsf(q1[e] - kt);
-          vv[e] += pe[e];
-        }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          d0s += __shfl_xor_sync(0xffffffffu, d0s, o);
-          d1s += __shfl_xor_sync(0xffffffffu, d1s, o);
-          l1s += __shfl_xor_sync(0xffffffffu, l1s, o);
-        }
-        const float s0 = d0s * 0.125f;
-        const float mn = fmaxf(m, s0);
-        const float resc = __expf(m - mn);  // first key: exp(-inf) = 0
-        const float pr = __expf(s0 - mn);
-        m = mn;
-        l = l * resc + pr;
-        // tanh(x) = 1 - 2/(1+exp(2x));  2*sigmoid(-y) = 2/(1+exp(y))
-        const float th = 1.f - 2.f / (1.f + __expf(0.25f * d1s));
-        const float a1 = th * (2.f / (1.f + __expf(0.125f * l1s)));
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc0[e] = fmaf(acc0[e], resc, pr * vv[e]);
-          acc1[e] = fmaf(a1, vv[e], acc1[e]);
-        }
-      }
-    }
-  }
-
-  // ---- combine the KS key subsets of this CTA
-  {
-    float* rec = dsm + (static_cast<int64_t>(ks) * H + head) * DEC_REC;
-    if ((lane & 7) == 0) {
-      rec[0] = m;
-      rec[1] = l;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      rec[2 + d0 + e] = acc0[e];
-      rec[66 + d0 + e] = acc1[e];
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < H * 64; i += blockDim.x) {
-    const int hh = i >> 6, d = i & 63;
-    float M = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < KS; ++w) M = fmaxf(M, dsm[(w * H + hh) * DEC_REC]);
-    float Ls = 0.f, a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < KS; ++w) {
-      const float* rec = dsm + (w * H + hh) * DEC_REC;
-      const float sc = (rec[0] == -INFINITY) ? 0.f : __expf(rec[0] - M);
-      Ls += rec[1] * sc;
-      a0 += rec[2 + d] * sc;
-      a1 += rec[66 + d];
-    }
-    float* o = out + hh * DEC_REC;
-    if (d == 0) {
-      o[0] = M;
-      o[1] = Ls;
-    }
-    o[2 + d] = a0;
-    o[66 + d] = a1;
-  }
-}
-
 // mix[b, h*64 + d] = 0.5 * acc0/l + 0.5 * acc1 over the T frame partials.  grid = B*H, 64 threads.
 __global__ void dec_attn_combine_kernel(const float* __restrict__ part, int T, int H, float* __restrict__ mix) {
   const int b = blockIdx.x / H, head = blockIdx.x % H, d = threadIdx.x;
@@ -184,9 +56,12 @@ __global__ void dec_attn_combine_kernel(const float* __restrict__ part, int T, i
   mix[(static_cast<int64_t>(b) * H + head) * 64 + d] = 0.5f * (a0 / Ls) + 0.5f * a1;
 }
 
-size_t dec_attn_workspace_bytes(int B, int T, int H) {
-  return static_cast<size_t>(B) * T * H * DEC_REC * sizeof(float);
-}
+size_t dec_attn_stream_workspace_bytes(int B, int T, int H);
+int decoder_attention_stream(const dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
+                             int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
+                             int T, int P, int H, float* part, int* recs_per_clip, cudaStream_t stream);
+
+size_t dec_attn_workspace_bytes(int B, int T, int H) { return dec_attn_stream_workspace_bytes(B, T, H); }
 
 int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                       int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B, int T, int P,
@@ -203,30 +78,10 @@ int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const 
   if (!workspace || workspace_bytes < need)
     return fail(DFD_ERR_WORKSPACE, "decoder_attention: workspace %zu < %zu bytes", workspace_bytes, need);
   float* part = static_cast<float*>(workspace);
-  const unsigned grid = static_cast<unsigned>(B) * T;
-  const __nv_bfloat16* kb = static_cast<const __nv_bfloat16*>(k);
-  const __nv_bfloat16* vb = static_cast<const __nv_bfloat16*>(v);
-#define DFD_LAUNCH_DEC(HH, KSV)                                                                                   \
-  do {                                                                                                            \
-    const size_t smem = static_cast<size_t>(KSV) * HH * DEC_REC * sizeof(float);                                  \
-    static bool configured = false;                                                                               \
-    if (!configured) {                                                                                            \
-      DFD_CUDA_OK(cudaFuncSetAttribute(dec_attn_partial_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                       (int)smem));                                                               \
-      configured = true;                                                                                          \
-    }                                                                                                             \
-    dec_attn_partial_kernel<HH><<<grid, (HH / 4) * KSV * 32, smem, stream>>>(qs, kb, vb, stride_b, stride_t,      \
-                                                                            stride_p, pos_emb, mask, T, P, part); \
-  } while (0)
-  switch (H) {
-    case 4: DFD_LAUNCH_DEC(4, 8); break;
-    case 8: DFD_LAUNCH_DEC(8, 4); break;
-    case 12: DFD_LAUNCH_DEC(12, 4); break;
-    default: DFD_LAUNCH_DEC(16, 3); break;
-  }
-#undef DFD_LAUNCH_DEC
-  DFD_CUDA_OK(cudaGetLastError());
-  dec_attn_combine_kernel<<<B * H, 64, 0, stream>>>(part, T, H, mix);
+  int recs = 0;
+  DFD_TRY(decoder_attention_stream(ctx, qs, k, v, stride_b, stride_t, stride_p, pos_emb, mask, B, T, P, H, part, &recs,
+                                   stream));
+  dec_attn_combine_kernel<<<B * H, 64, 0, stream>>>(part, recs, H, mix);
   DFD_CUDA_OK(cudaGetLastError());
   (void)ctx;
   return 0;

@@ -182,7 +182,8 @@ int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, in
                        float* logits, void* stream);
 
 /* One decoder attention call on its own (models.py:136-146 without in/out projections), for unit tests:
- * qs fp32 [B, H, 128] = per head [smax query(64) | coda query(64)]; mix fp32 [B, H*64]. */
+ * qs fp32 [B, H, 128] = per head [smax query(64) | coda query(64)]; mix fp32 [B, H*64].
+ * workspace: at least 2*B*T*H*130*4 bytes (partial records of the streaming kernel). */
 int dfd_decoder_attention(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                           int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
                           int T, int P, int H, float* mix, void* workspace, size_t workspace_bytes, void* stream);

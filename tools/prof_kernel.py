@@ -34,6 +34,17 @@ elif which.startswith("gemm"):
     fn = lambda: nat.gemm_bf16(a, w, bias, out, epi)
     flops = 2 * M * n * k
     nbytes = M * k * 2 + M * n * (8 if epi == 3 else 2)
+elif which == "dec_attn":
+    B, T, P = 64, 8, 196
+    qkv = rnd(B * T * L, 3 * D)
+    view = qkv.view(B, T, L, 3, H, 64)
+    k, v = view[:, :, 1:, 1], view[:, :, 1:, 2]
+    qs = rnd(B, H, 128, dtype=torch.float32)
+    pe = rnd(T, H, 64, scale=0.05, dtype=torch.float32)
+    mask = torch.ones(B, T, dtype=torch.bool, device=dev)
+    fn = lambda: nat.decoder_attention(qs, k, v, pe, mask)
+    flops = 0
+    nbytes = 2 * B * T * P * D * 2
 elif which == "ln":
     x = rnd(M, D, dtype=torch.float32)
     gam, bet = rnd(D, dtype=torch.float32), rnd(D, dtype=torch.float32)
