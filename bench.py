@@ -231,6 +231,7 @@ def run_b200(args, rank, world, local_rank):
     x, m = x_host.to(dev), m_host.to(dev)
     gathered = [torch.empty((clips, 2), device=dev) for _ in range(world)] if dist else None
 
+    @torch.no_grad()  # as every inference caller of the reference does (inference.py:65, evaluator.py:50)
     def step():
         logits, _ = det.predict(x, m)
         if dist:

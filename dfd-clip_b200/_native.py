@@ -23,6 +23,7 @@ EXPORTS = (
     "dfd_encoder_packed_bytes", "dfd_encoder_workspace_bytes", "dfd_encoder_pack_weights", "dfd_encoder_forward",
     "dfd_decoder_workspace_bytes", "dfd_decoder_forward", "dfd_project_logits", "dfd_decoder_attention",
     "dfd_timing_enable", "dfd_timing_read", "dfd_timing_num_tags", "dfd_timing_tag_name",
+    "dfd_decoder_attention_workspace_bytes", "dfd_decoder_attention_train", "dfd_decoder_attention_backward",
 )
 
 
@@ -102,6 +103,14 @@ def load_library():
         lib.dfd_decoder_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                               c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                               c_size_t, c_void_p]
+        lib.dfd_decoder_attention_workspace_bytes.argtypes = [c_int, c_int, c_int]
+        lib.dfd_decoder_attention_workspace_bytes.restype = c_size_t
+        lib.dfd_decoder_attention_train.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                                    c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                                    c_void_p, c_void_p, c_size_t, c_void_p]
+        lib.dfd_decoder_attention_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                                       c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                                       c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
         lib.dfd_timing_enable.argtypes = [c_void_p, c_int]
         lib.dfd_timing_read.argtypes = [c_void_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_int)]
         lib.dfd_timing_tag_name.argtypes = [c_int]
@@ -240,3 +249,42 @@ def project_logits(feature, proj, scale=5.0):
     check(load_library().dfd_project_logits(ctx(feature.device), ptr(feature.contiguous()), ptr(proj.contiguous()),
                                             b, d, o, scale, ptr(out), stream_ptr(feature.device)))
     return out
+
+
+def _check_kv(k, v):
+    b, t, p, h, dh = k.shape
+    assert dh == 64 and k.stride(4) == 1 and k.stride(3) == 64 and k.stride() == v.stride()
+    assert k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
+    return b, t, p, h
+
+
+def decoder_attention_train(qs, k, v, pos_emb, mask):
+    """decoder_attention that also returns the per-(clip, head) statistics [B,H,66] the backward pass needs."""
+    b, t, p, h = _check_kv(k, v)
+    lib = load_library()
+    m8 = mask.to(torch.uint8).contiguous()
+    mix = torch.empty((b, h * 64), dtype=torch.float32, device=k.device)
+    stats = torch.empty((b, h, 66), dtype=torch.float32, device=k.device)
+    nbytes = lib.dfd_decoder_attention_workspace_bytes(b, t, h)
+    ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=k.device)
+    check(lib.dfd_decoder_attention_train(
+        ctx(k.device), ptr(qs.contiguous()), ptr(k), ptr(v), k.stride(0), k.stride(1), k.stride(2),
+        ptr(None if pos_emb is None else pos_emb.contiguous()), ptr(m8), b, t, p, h, ptr(mix), ptr(stats), ptr(ws),
+        nbytes, stream_ptr(k.device)))
+    return mix, stats
+
+
+def decoder_attention_backward(qs, k, v, pos_emb, mask, stats, dmix):
+    """(dqs [B,H,128], dpos_emb [T,H,64] or None) for dmix [B,H*64]; K and V are constants (frozen encoder)."""
+    b, t, p, h = _check_kv(k, v)
+    lib = load_library()
+    m8 = mask.to(torch.uint8).contiguous()
+    dqs = torch.empty((b, h, 128), dtype=torch.float32, device=k.device)
+    dpe = None if pos_emb is None else torch.empty((t, h, 64), dtype=torch.float32, device=k.device)
+    nbytes = lib.dfd_decoder_attention_workspace_bytes(b, t, h)
+    ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=k.device)
+    check(lib.dfd_decoder_attention_backward(
+        ctx(k.device), ptr(qs.contiguous()), ptr(k), ptr(v), k.stride(0), k.stride(1), k.stride(2),
+        ptr(None if pos_emb is None else pos_emb.contiguous()), ptr(m8), ptr(stats.contiguous()),
+        ptr(dmix.contiguous().float()), b, t, p, h, ptr(dqs), ptr(dpe), ptr(ws), nbytes, stream_ptr(k.device)))
+    return dqs, dpe

@@ -39,7 +39,9 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
 }
 
 // mix[b, h*64 + d] = 0.5 * acc0/l + 0.5 * acc1 over the T frame partials.  grid = B*H, 64 threads.
-__global__ void dec_attn_combine_kernel(const float* __restrict__ part, int T, int H, float* __restrict__ mix) {
+// stats (optional, for the backward pass): [B, H, 66] = (M, L, o0[64]) with o0 = softmax-weighted mean of V~.
+__global__ void dec_attn_combine_kernel(const float* __restrict__ part, int T, int H, float* __restrict__ mix,
+                                        float* __restrict__ stats = nullptr) {
   const int b = blockIdx.x / H, head = blockIdx.x % H, d = threadIdx.x;
   float M = -INFINITY;
   for (int t = 0; t < T; ++t) M = fmaxf(M, part[((static_cast<int64_t>(b) * T + t) * H + head) * DEC_REC]);
@@ -54,6 +56,14 @@ __global__ void dec_attn_combine_kernel(const float* __restrict__ part, int T, i
     a1 += rec[66 + d];
   }
   mix[(static_cast<int64_t>(b) * H + head) * 64 + d] = 0.5f * (a0 / Ls) + 0.5f * a1;
+  if (stats) {
+    float* st = stats + (static_cast<int64_t>(b) * H + head) * 66;
+    if (d == 0) {
+      st[0] = M;
+      st[1] = Ls;
+    }
+    st[2 + d] = a0 / Ls;
+  }
 }
 
 size_t dec_attn_stream_workspace_bytes(int B, int T, int H);
@@ -65,7 +75,8 @@ size_t dec_attn_workspace_bytes(int B, int T, int H) { return dec_attn_stream_wo
 
 int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                       int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B, int T, int P,
-                      int H, float* mix, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                      int H, float* mix, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                      float* stats = nullptr) {
   DFD_CHECK_ARG(B >= 0 && T > 0 && P > 0, "decoder_attention: bad shape B=%d T=%d P=%d", B, T, P);
   if (B == 0) return 0;
   DFD_CHECK_ARG(qs && k && v && mask && mix, "decoder_attention: null pointer");
@@ -81,7 +92,7 @@ int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const 
   int recs = 0;
   DFD_TRY(decoder_attention_stream(ctx, qs, k, v, stride_b, stride_t, stride_p, pos_emb, mask, B, T, P, H, part, &recs,
                                    stream));
-  dec_attn_combine_kernel<<<B * H, 64, 0, stream>>>(part, recs, H, mix);
+  dec_attn_combine_kernel<<<B * H, 64, 0, stream>>>(part, recs, H, mix, stats);
   DFD_CUDA_OK(cudaGetLastError());
   (void)ctx;
   return 0;

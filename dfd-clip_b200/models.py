@@ -100,6 +100,30 @@ class Transformer(nn.Module):
         ])
 
 
+class _DecoderAttentionFn(torch.autograd.Function):
+    """Decoder cross-attention (reference :136-146 without the projections) with native forward and backward.
+    K and V are the frozen encoder's taps: no gradient flows into them."""
+
+    @staticmethod
+    def forward(ctx, qs, pos_emb, k, v, mask):
+        pe = None if pos_emb is None else pos_emb.detach().reshape(pos_emb.shape[0], -1, 64)
+        mix, stats = _native.decoder_attention_train(qs.detach(), k, v, pe, mask)
+        ctx.save_for_backward(qs.detach(), stats, mask)
+        ctx.kv = (k, v)
+        ctx.pe = pe
+        ctx.pe_shape = None if pos_emb is None else pos_emb.shape
+        return mix
+
+    @staticmethod
+    def backward(ctx, dmix):
+        qs, stats, mask = ctx.saved_tensors
+        k, v = ctx.kv
+        dqs, dpe = _native.decoder_attention_backward(qs, k, v, ctx.pe, mask, stats, dmix)
+        if dpe is not None:
+            dpe = dpe.reshape(ctx.pe_shape)
+        return dqs, dpe, None, None, None
+
+
 class Decoder(nn.Module):
     """Temporal decoder: a learnable CLS query cross-attends (softmax + CoDA) to the tapped K/V of all T*P patch
     tokens of a clip, block by block, then ``ln_post`` and the task projection(s) (reference :272-361)."""
@@ -170,6 +194,31 @@ class Decoder(nn.Module):
         """kvs: list (one per tapped layer) of ``{k, v: [B, T, P, H, 64]}``; m: bool [B, T].
         Returns ``(task_logits, video_feature)`` like the reference (:323-361); logits are NOT yet normalised."""
         return self.run(kvs, m, logit_scale=0.0)
+
+    def run_autograd(self, kvs, m, logit_scale=0.0):
+        """Differentiable ``run`` for the training step (reference :568-596 with ``train=True``): the K/V-streaming
+        attention uses the native forward/backward kernels; the one-token-per-clip LayerNorm / linear layers are
+        evaluated with torch ops in fp32 so that autograd produces the parameter gradients (SGD step, DDP
+        all-reduce) exactly as in the reference's trainer. Gradients never reach the frozen encoder."""
+        k0 = kvs[0]["k"]
+        b, t, p = k0.shape[:3]
+        h, d = self.heads, self.width
+        if k0.device.type != "cuda":
+            raise _native.NativeError("dfdclip_b200 decoder needs CUDA tensors (no CPU fallback)")
+        x = self.ln_pre(self.class_embedding.view(1, d)).expand(b, d)
+        for blk, kv in zip(self.transformer.resblocks, kvs):
+            qs = blk.attn.in_proj(blk.ln_1(x)).view(b, h, 128)
+            mix = _DecoderAttentionFn.apply(qs, self.positional_embedding, kv["k"].detach(), kv["v"].detach(), m)
+            x = x + blk.attn.out_proj(mix)
+            x = x + blk.mlp(blk.ln_2(x))
+        video_feature = self.ln_post(x)
+        task_logits = []
+        for mats in self.task_projections:
+            l = video_feature @ mats[-1]
+            if logit_scale > 0:
+                l = logit_scale * l / (torch.norm(l, dim=-1, keepdim=True) + 1e-10)
+            task_logits.append(l)
+        return task_logits, video_feature
 
     def run(self, kvs, m, logit_scale=0.0):
         """``forward`` with the logit normalisation of ``Detector.predict`` (:551-553) fused into the projection
@@ -320,9 +369,11 @@ class Detector(nn.Module):
         """Second half of ``predict``: decoder + logit normalisation on already-encoded taps (``qkv[layer]`` =
         packed bf16 ``[B*T*L, 3D]`` buffers from ``encoder.encode``)."""
         kvs = self.taps_from_qkv(qkv, b, t)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()) and train:
-            raise NotImplementedError("the decoder backward (training step) is not implemented yet on the B200 path")
-        task_logits, video_features = self.decoder.run(kvs, m, logit_scale=5.0)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()):
+            # training step (or any caller that wants decoder gradients): differentiable decoder
+            task_logits, video_features = self.decoder.run_autograd(kvs, m, logit_scale=5.0)
+        else:
+            task_logits, video_features = self.decoder.run(kvs, m, logit_scale=5.0)
         features = {}
         if with_video_features:
             features["video"] = video_features

@@ -188,6 +188,27 @@ int dfd_decoder_attention(dfd_ctx* ctx, const float* qs, const void* k, const vo
                           int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
                           int T, int P, int H, float* mix, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Training step (config C5): the encoder is frozen, so only the decoder needs gradients. The decoder attention is
+ * the one op of the head that streams the K/V taps; its forward-with-statistics and its backward are native, the
+ * 1-token-per-clip linear / LayerNorm layers around it run under torch autograd (src/models.py:568-596 + autograd).
+ * ---------------------------------------------------------------------------------------------------- */
+size_t dfd_decoder_attention_workspace_bytes(int B, int T, int H);
+
+/* dfd_decoder_attention that also saves, per (clip, head), stats fp32 [B, H, 66] = (softmax max M, softmax sum L,
+ * o0[64] = softmax-weighted mean of V + pe) for the backward pass. */
+int dfd_decoder_attention_train(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
+                                int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
+                                int T, int P, int H, float* mix, float* stats, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/* Gradients of the decoder attention w.r.t. the queries (dqs fp32 [B, H, 128]) and the temporal position embedding
+ * (dpos_emb fp32 [T, H, 64], NULL iff pos_emb is NULL) given dmix fp32 [B, H*64]; K and V are constants. */
+int dfd_decoder_attention_backward(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
+                                   int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask,
+                                   const float* stats, const float* dmix, int B, int T, int P, int H, float* dqs,
+                                   float* dpos_emb, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,3 +18,14 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _inference_mode_by_default():
+    """Every caller of the hot path in the reference runs under torch.no_grad (inference.py:65, evaluator.py:50,
+    pipeline.py:288); tests do the same. The training-step tests re-enable grad locally."""
+    import torch
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(prev)

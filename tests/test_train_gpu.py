@@ -1,0 +1,120 @@
+"""Training step (BASELINE config C5): frozen encoder forward with K/V taps + decoder forward/backward.
+The CUDA path (native attention forward/backward inside torch autograd) is compared with the oracle's autograd."""
+import pytest
+import torch
+
+from helpers import cosine, load_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _attention_ref(qs, k, v, pe, mask):
+    """fp32 restatement of src/models.py:99-146 (smax + coda, no projections), differentiable."""
+    b, t, p, h, dh = k.shape
+    k = k.float()
+    v = v.float()
+    if pe is not None:
+        k = k + pe.view(1, t, 1, h, dh)
+        v = v + pe.view(1, t, 1, h, dh)
+    k = k.flatten(1, 2)
+    v = v.flatten(1, 2)
+    m = mask.repeat_interleave(p, dim=-1).unsqueeze(1).unsqueeze(-1)
+    q0 = qs[:, :, :64].unsqueeze(1)
+    q1 = qs[:, :, 64:].unsqueeze(1)
+    aff0 = torch.einsum("nqhc,nkhc->nqkh", q0 / 8.0, k).masked_fill(~m, float("-inf")).softmax(dim=-2)
+    aff1 = torch.einsum("nqhc,nkhc->nqkh", q1 / 8.0, k).tanh()
+    gate = -(q1 - k).abs().sum(-1).unsqueeze(1) / 8.0
+    gate = 2 * gate.sigmoid().masked_fill(~m, 0.0)
+    aff = (aff0 + aff1 * gate) / 2
+    return torch.einsum("nqlh,nlhc->nqhc", aff, v).flatten(-2).squeeze(1)
+
+
+@pytest.mark.parametrize("b,t,p,h", [(2, 8, 196, 12), (3, 4, 50, 16), (2, 3, 17, 4), (4, 2, 196, 8)])
+@pytest.mark.parametrize("use_pe", [True, False])
+def test_decoder_attention_backward(cuda_device, b, t, p, h, use_pe):
+    from dfdclip_b200 import _native as nat
+    g = torch.Generator(device="cpu").manual_seed(b * 10 + t)
+    d = h * 64
+    buf = torch.randn(b * t * (p + 1), 3 * d, generator=g).to(cuda_device, torch.bfloat16)
+    view = buf.view(b, t, p + 1, 3, h, 64)
+    k, v = view[:, :, 1:, 1], view[:, :, 1:, 2]
+    qs = (torch.randn(b, h, 128, generator=g) * 0.7).to(cuda_device)
+    pe = (torch.randn(t, h, 64, generator=g) * 0.3).to(cuda_device) if use_pe else None
+    mask = torch.ones(b, t, dtype=torch.bool, device=cuda_device)
+    if t > 1:
+        mask[0, -1] = False
+    dmix = torch.randn(b, d, generator=g).to(cuda_device)
+
+    mix, stats = nat.decoder_attention_train(qs, k, v, pe, mask)
+    dqs, dpe = nat.decoder_attention_backward(qs, k, v, pe, mask, stats, dmix)
+    torch.cuda.synchronize()
+
+    with torch.enable_grad():
+        qs_r = qs.clone().requires_grad_(True)
+        pe_r = pe.clone().requires_grad_(True) if use_pe else None
+        ref = _attention_ref(qs_r, k, v, pe_r, mask)
+        ref.backward(dmix)
+    assert (mix - ref.detach()).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert cosine(dqs, qs_r.grad) > 0.9999
+    assert (dqs - qs_r.grad).abs().max().item() < 2e-3 * max(1e-3, qs_r.grad.abs().max().item())
+    if use_pe:
+        assert cosine(dpe, pe_r.grad) > 0.9999
+        assert (dpe - pe_r.grad).abs().max().item() < 2e-3 * max(1e-3, pe_r.grad.abs().max().item())
+    else:
+        assert dpe is None
+
+
+def test_training_step_matches_oracle_autograd(cuda_device):
+    """loss = mean CE(5 l/|l|, y) through Detector.forward(train=True); gradients of every decoder parameter against
+    the oracle's autograd (fp32, CPU) on the same weights and clips; one SGD step then lowers the loss."""
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.models import Detector
+    oracle = load_oracle()
+    arch, frames, clips = "small-512x6", 3, 4
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:" + arch
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    det = Detector(cfg, frames, None)
+    sd = synthetic.detector_state_dict(arch, frames, out_dims=(2,), taps=det.layer_indices, seed=0)
+    det.load_state_dict(sd, strict=True)
+    det = det.to(cuda_device).train()
+    x, m = synthetic.make_clips(clips, frames, synthetic.vit_dims(arch)["image_size"], seed=5)
+    y = torch.tensor([0, 1, 1, 0])
+
+    with torch.enable_grad():
+        losses, logits, other = det(x.to(cuda_device), [y.to(cuda_device)], m.to(cuda_device), train=True,
+                                    single_task=0)
+        assert other == {}
+        loss = losses[0].mean()
+        loss.backward()
+        # oracle: same computation in fp32 on the CPU with autograd on the decoder parameters
+        sd_r = {k_: (v_.clone().requires_grad_(True) if k_.startswith("decoder.") else v_) for k_, v_ in sd.items()}
+        ref_logits, _ = oracle.detector_predict(sd_r, x, m, det.layer_indices, (2,))
+        ref_loss = oracle.detector_eval_losses(ref_logits, [y])[0].mean()
+        ref_loss.backward()
+
+    assert abs(loss.item() - ref_loss.item()) < 2e-2
+    assert all(not p.requires_grad and p.grad is None for p in det.encoder.parameters())
+    checked = 0
+    for name, p in det.decoder.named_parameters():
+        ref_g = sd_r["decoder." + name].grad
+        assert p.grad is not None, name
+        assert ref_g is not None, name
+        if ref_g.abs().max().item() < 1e-7:
+            assert p.grad.abs().max().item() < 1e-4, name
+            continue
+        assert cosine(p.grad.cpu(), ref_g) > 0.995, (name, cosine(p.grad.cpu(), ref_g))
+        rel = (p.grad.cpu() - ref_g).norm().item() / ref_g.norm().item()
+        assert rel < 0.1, (name, rel)
+        checked += 1
+    assert checked >= 30
+
+    # one SGD step (reference: configure_optimizers -> SGD momentum 0.95) lowers the loss on the same batch
+    with torch.enable_grad():
+        g2 = sum(p.grad.double().pow(2).sum().item() for p in det.decoder.parameters())
+        opt = det.configure_optimizers(lr=0.05 / g2)  # first-order decrease of 0.05: a small step along -grad
+        opt.step()
+        opt.zero_grad()
+        losses2, _, _ = det(x.to(cuda_device), [y.to(cuda_device)], m.to(cuda_device), train=True, single_task=0)
+    assert losses2[0].mean().item() < loss.item()
