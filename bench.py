@@ -306,10 +306,20 @@ def run_b200(args, rank, world, local_rank):
     gemm_ms_per_step = sum(kernel_ms[k][0] for k in gemm_tags) / args.steps
     gemm_launches = sum(kernel_ms[k][1] for k in gemm_tags) / args.steps
     achieved = gemm_flops * clips / (gemm_ms_per_step * 1e-3) / 1e12 if gemm_ms_per_step > 0 else None
+    # DRAM traffic of the GEMM family per launch, from the committed ncu capture of the same step (not measured live)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    if os.path.exists(tpath) and args.arch == "ViT-B/16" and clips == 64 and frames == 8:
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        tsum = sum(tj[k] * kernel_ms[k][1] for k in gemm_tags if k in tj)
+        tcnt = sum(kernel_ms[k][1] for k in gemm_tags if k in tj)
+        traffic = tsum / tcnt if tcnt else None
     roofline = {
-        "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all epilogues)", "achieved": achieved,
+        "bound": "tensor", "kernel": "gemm_bf16_2sm_kernel (tcgen05 cta_group::2, all epilogues)", "achieved": achieved,
         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
-        "peak_source": "%s (sustained bf16 GEMM)" % peaks["source"], "traffic": None,
+        "peak_source": "%s (sustained bf16 GEMM)" % peaks["source"], "traffic": traffic,
+        "traffic_note": "average DRAM bytes per GEMM launch (ncu capture in profiles/r1b_kernels.md)",
         "launches_per_step": gemm_launches, "ms_per_step": gemm_ms_per_step,
         "share_of_step": gemm_ms_per_step / (elapsed_ms / args.steps),
         "whole_step_tflops": total_flops * clips * world / (elapsed_ms / args.steps * 1e-3) / 1e12 / world,
