@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libdfdclip_b200.so")
 c_void_p, c_int, c_int64, c_size_t, c_float = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float)
 
-EPI_STORE_BF16, EPI_STORE_BF16_QGELU, EPI_STORE_F32, EPI_ADD_F32 = 0, 1, 2, 3
+EPI_STORE_BF16, EPI_STORE_BF16_QGELU, EPI_STORE_F32, EPI_ADD_F32, EPI_ADD_BF16, EPI_STORE_BF16_GELU = 0, 1, 2, 3, 4, 5
+ADAPTER_GELU_LN, ADAPTER_LN_GELU, ADAPTER_NLN, ADAPTER_XXX, ADAPTER_LINEAR = 0, 1, 2, 3, 4
 
 # Every symbol include/dfdclip_b200.h declares (tests check the library exports each of them).
 EXPORTS = (
@@ -24,6 +25,7 @@ EXPORTS = (
     "dfd_decoder_workspace_bytes", "dfd_decoder_forward", "dfd_project_logits", "dfd_decoder_attention",
     "dfd_timing_enable", "dfd_timing_read", "dfd_timing_num_tags", "dfd_timing_tag_name",
     "dfd_decoder_attention_workspace_bytes", "dfd_decoder_attention_train", "dfd_decoder_attention_backward",
+    "dfd_adapter_workspace_bytes", "dfd_adapter_apply",
 )
 
 
@@ -57,6 +59,10 @@ class DecoderWeights(ctypes.Structure):
 
 class KvTaps(ctypes.Structure):
     _fields_ = [("k", _PP), ("v", _PP), ("stride_b", c_int64), ("stride_t", c_int64), ("stride_p", c_int64)]
+
+
+class AdapterWeights(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w_down", "w_mid", "w_up", "ln_weight", "ln_bias")]
 
 
 _lib = None
@@ -111,6 +117,10 @@ def load_library():
         lib.dfd_decoder_attention_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                                        c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+        lib.dfd_adapter_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int64]
+        lib.dfd_adapter_workspace_bytes.restype = c_size_t
+        lib.dfd_adapter_apply.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdapterWeights), c_void_p,
+                                          c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]
         lib.dfd_timing_enable.argtypes = [c_void_p, c_int]
         lib.dfd_timing_read.argtypes = [c_void_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_int)]
         lib.dfd_timing_tag_name.argtypes = [c_int]
@@ -288,3 +298,20 @@ def decoder_attention_backward(qs, k, v, pos_emb, mask, stats, dmix):
         ptr(None if pos_emb is None else pos_emb.contiguous()), ptr(m8), ptr(stats.contiguous()),
         ptr(dmix.contiguous().float()), b, t, p, h, ptr(dqs), ptr(dpe), ptr(ws), nbytes, stream_ptr(k.device)))
     return dqs, dpe
+
+
+def adapter_apply(kind, kv, rows, ld, width, inner, w_down, w_mid, w_up, ln_weight, ln_bias, group_rows, group_skip,
+                  workspace=None):
+    """In-place CompInvAdapter on one bf16 tap: ``kv`` is a tensor whose data pointer is the first element of a
+    ``[rows, width]`` matrix with row pitch ``ld`` elements (a K or V column slice of a packed QKV buffer).
+    Weights: bf16 matrices, fp32 LayerNorm parameters. Returns the workspace tensor (reusable)."""
+    lib = load_library()
+    dev = kv.device
+    assert kv.dtype == torch.bfloat16
+    nbytes = lib.dfd_adapter_workspace_bytes(kind, width, inner, rows)
+    if workspace is None or workspace.numel() < nbytes or workspace.device != dev:
+        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    w = AdapterWeights(ptr(w_down).value, ptr(w_mid).value, ptr(w_up).value, ptr(ln_weight).value, ptr(ln_bias).value)
+    check(lib.dfd_adapter_apply(ctx(dev), kind, width, inner, ctypes.byref(w), ptr(kv), ld, rows, group_rows,
+                                group_skip, ptr(workspace), workspace.numel(), stream_ptr(dev)))
+    return workspace

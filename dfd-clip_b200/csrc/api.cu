@@ -153,7 +153,7 @@ int dfd_timing_num_tags(void) { return DFD_TAG_COUNT; }
 const char* dfd_timing_tag_name(int tag) {
   static const char* names[DFD_TAG_COUNT] = {"patchify",  "gemm_patch_embed", "layernorm",  "gemm_qkv",
                                              "mha",       "gemm_out_proj",    "gemm_c_fc",  "gemm_c_proj",
-                                             "dec_attn",  "dec_linear",       "dec_other"};
+                                             "dec_attn",  "dec_linear",       "dec_other",  "adapter"};
   return (tag >= 0 && tag < DFD_TAG_COUNT) ? names[tag] : "?";
 }
 

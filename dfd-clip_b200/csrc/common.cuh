@@ -256,6 +256,9 @@ __device__ __forceinline__ float quick_gelu_fast(float x) {
   return x * fmaf(0.5f, t, 0.5f);
 }
 
+// nn.GELU() (exact, erf form): the adapter's activation, src/models.py:803, 893
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -186,6 +186,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v1 = quick_gelu_fast(v1);
                 v2 = quick_gelu_fast(v2);
                 v3 = quick_gelu_fast(v3);
+              } else if constexpr (EPI == DFD_EPI_STORE_BF16_GELU) {
+                v0 = gelu_erf(v0);
+                v1 = gelu_erf(v1);
+                v2 = gelu_erf(v2);
+                v3 = gelu_erf(v3);
               }
               packed[half * 16 + j / 2 + 0] = pack_bf16(v0, v1);
               packed[half * 16 + j / 2 + 1] = pack_bf16(v2, v3);
@@ -210,7 +215,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && row0 < M) {
-          if constexpr (EPI == DFD_EPI_ADD_F32)
+          if constexpr (EPI == DFD_EPI_ADD_F32 || EPI == DFD_EPI_ADD_BF16)
             tma_reduce_add_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
           else
             tma_store_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
@@ -466,6 +471,11 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 v1 = quick_gelu_fast(v1);
                 v2 = quick_gelu_fast(v2);
                 v3 = quick_gelu_fast(v3);
+              } else if constexpr (EPI == DFD_EPI_STORE_BF16_GELU) {
+                v0 = gelu_erf(v0);
+                v1 = gelu_erf(v1);
+                v2 = gelu_erf(v2);
+                v3 = gelu_erf(v3);
               }
               packed[half * 16 + j / 2 + 0] = pack_bf16(v0, v1);
               packed[half * 16 + j / 2 + 1] = pack_bf16(v2, v3);
@@ -489,7 +499,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && row0 < M) {
-          if constexpr (EPI == DFD_EPI_ADD_F32)
+          if constexpr (EPI == DFD_EPI_ADD_F32 || EPI == DFD_EPI_ADD_BF16)
             tma_reduce_add_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
           else
             tma_store_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
@@ -587,6 +597,10 @@ int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int
         return launch2<DFD_EPI_STORE_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
       case DFD_EPI_ADD_F32:
         return launch2<DFD_EPI_ADD_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+      case DFD_EPI_ADD_BF16:
+        return launch2<DFD_EPI_ADD_BF16>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+      case DFD_EPI_STORE_BF16_GELU:
+        return launch2<DFD_EPI_STORE_BF16_GELU>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
       default:
         return fail(DFD_ERR_INVALID, "gemm: unknown epilogue %d", epilogue);
     }
@@ -600,6 +614,10 @@ int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int
       return launch<DFD_EPI_STORE_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
     case DFD_EPI_ADD_F32:
       return launch<DFD_EPI_ADD_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+    case DFD_EPI_ADD_BF16:
+      return launch<DFD_EPI_ADD_BF16>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
+    case DFD_EPI_STORE_BF16_GELU:
+      return launch<DFD_EPI_STORE_BF16_GELU>(ctx, tmA, tmB, tmC, bias, M, N, K, stream);
     default:
       return fail(DFD_ERR_INVALID, "gemm: unknown epilogue %d", epilogue);
   }

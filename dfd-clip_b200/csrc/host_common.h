@@ -27,6 +27,7 @@ enum {
   DFD_TAG_DEC_ATTN,
   DFD_TAG_DEC_LINEAR,
   DFD_TAG_DEC_OTHER,
+  DFD_TAG_ADAPTER,
   DFD_TAG_COUNT
 };
 

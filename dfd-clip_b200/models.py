@@ -3,8 +3,9 @@
 (SURVEY App. B.3), computing on the B200 through libdfdclip_b200.so.
 
 Supported configuration = the reference's defaults (``Detector.get_default_config`` :406-431): CLIP foundation,
-stride or index taps, ``op_mode.temporal_position`` on or off, no adapter, empty ``train_mode``. Every other knob
-raises ``NotImplementedError`` instead of silently diverging. There is no CPU / PyTorch fallback for the encoder
+stride or index taps, ``op_mode.temporal_position`` on or off, empty ``train_mode`` — plus the ``CompInvAdapter``
+(:783-940) of the shipped configs in inference (and frozen in training). Every other knob raises
+``NotImplementedError`` instead of silently diverging. There is no CPU / PyTorch fallback for the encoder
 or the decoder attention.
 """
 import ctypes
@@ -137,8 +138,7 @@ class Decoder(nn.Module):
         for key in _UNSUPPORTED_OP_MODES:
             if key in config.op_mode and config.op_mode[key]:
                 raise NotImplementedError("op_mode.%s is not implemented by the B200 path" % key)
-        if config.dropout:
-            raise NotImplementedError("dropout > 0 is not implemented by the B200 path")
+        self.dropout = float(config.dropout)
         scale = width ** -0.5
         self.class_embedding = nn.Parameter(scale * torch.randn(width))
         if "temporal_position" in config.op_mode and config.op_mode.temporal_position:
@@ -146,9 +146,11 @@ class Decoder(nn.Module):
         else:
             self.positional_embedding = None
         self.ln_pre = LayerNorm(width)
+        self.drop_pre = nn.Dropout(config.dropout)
         self.transformer = Transformer(width, heads, config, num_frames, layer_indices=detector.layer_indices,
                                        reference_layers=detector.encoder.transformer.resblocks)
         self.ln_post = LayerNorm(width)
+        self.drop_post = nn.Dropout(config.dropout)
         self.task_projections = []
         for i, output_dim in enumerate(config.out_dim):
             name = f"proj{i}x{output_dim}"
@@ -205,13 +207,13 @@ class Decoder(nn.Module):
         h, d = self.heads, self.width
         if k0.device.type != "cuda":
             raise _native.NativeError("dfdclip_b200 decoder needs CUDA tensors (no CPU fallback)")
-        x = self.ln_pre(self.class_embedding.view(1, d)).expand(b, d)
+        x = self.drop_pre(self.ln_pre(self.class_embedding.view(1, d)).expand(b, d))
         for blk, kv in zip(self.transformer.resblocks, kvs):
             qs = blk.attn.in_proj(blk.ln_1(x)).view(b, h, 128)
             mix = _DecoderAttentionFn.apply(qs, self.positional_embedding, kv["k"].detach(), kv["v"].detach(), m)
             x = x + blk.attn.out_proj(mix)
             x = x + blk.mlp(blk.ln_2(x))
-        video_feature = self.ln_post(x)
+        video_feature = self.drop_post(self.ln_post(x))
         task_logits = []
         for mats in self.task_projections:
             l = video_feature @ mats[-1]
@@ -279,6 +281,146 @@ class Decoder(nn.Module):
         return task_logits, video_feature
 
 
+class CompInvAdapter(nn.Module):
+    """Compression-invariant adapter on the tapped K/V (reference :783-940): per tapped layer ``i`` and per ``k``/``v``
+    one ``nn.Sequential`` bottleneck named ``l{i}_{k|v}`` (same module layout, hence the same ``state_dict`` keys as
+    the reference), applied with a residual connection — natively and IN PLACE on the encoder's bf16 tap buffers
+    (``dfd_adapter_apply``: two tcgen05 GEMMs and one row kernel per tap)."""
+
+    _STRUCTS = {
+        "768-x-768": _native.ADAPTER_GELU_LN,
+        "legacy-768-x-768": _native.ADAPTER_GELU_LN,
+        "768-x-768-nln": _native.ADAPTER_NLN,
+        "768-x-768-ln": _native.ADAPTER_LN_GELU,
+        "768-x-768-z0": _native.ADAPTER_LN_GELU,
+        "768-xxx-768": _native.ADAPTER_XXX,
+        "linear": _native.ADAPTER_LINEAR,
+    }
+
+    def __init__(self, config, detector, num_frames=50):
+        super().__init__()
+        width = detector.encoder.width
+        patches = (detector.encoder.input_resolution // detector.encoder.patch_size) ** 2
+        kind = config.adapter.struct.type
+        if kind == "768-bn":
+            raise NotImplementedError("adapter.struct.type='768-bn' (BatchNorm2d over frames) is not implemented "
+                                      "by the B200 path")
+        if kind not in self._STRUCTS:
+            raise NotImplementedError("unknown adapter.struct.type %r" % (kind,))
+        self.struct_type = kind
+        self.kind = self._STRUCTS[kind]
+        self.width, self.patches = width, patches
+        self.inner = width if kind == "linear" else int(config.adapter.struct.x)
+        if self.inner % 256 != 0 or self.inner > 1024:
+            raise NotImplementedError("adapter.struct.x=%d: the B200 path needs 256, 512, 768 or 1024" % self.inner)
+        self.residual = kind != "linear"
+        self.dropout = float(config.dropout)
+        self.layer_blocks = []
+        x, p = self.inner, config.dropout
+        for i in range(len(detector.layer_indices)):
+            blk = {}
+            for j in ("k", "v"):
+                if kind == "768-x-768":
+                    mod = nn.Sequential(nn.Linear(width, x, bias=False), nn.GELU(), nn.LayerNorm(x), nn.Dropout(p / 5),
+                                        nn.Linear(x, width, bias=False), nn.Dropout(p))
+                elif kind == "legacy-768-x-768":
+                    mod = nn.Sequential(nn.Linear(width, x, bias=False), nn.GELU(), nn.LayerNorm(x),
+                                        nn.Linear(x, width, bias=False), nn.Dropout(p))
+                elif kind == "768-x-768-nln":
+                    mod = nn.Sequential(nn.Linear(width, x, bias=False), nn.LayerNorm((patches, x)), nn.GELU(),
+                                        nn.Dropout(p / 10), nn.Linear(x, width, bias=False), nn.Dropout(p))
+                elif kind in ("768-x-768-ln", "768-x-768-z0"):
+                    mod = nn.Sequential(nn.Linear(width, x, bias=False), nn.LayerNorm(x), nn.GELU(),
+                                        nn.Dropout(p / 10), nn.Linear(x, width, bias=False), nn.Dropout(p))
+                    if kind == "768-x-768-z0":  # identity at initialisation (reference :856-858)
+                        mod[1].weight.data.zero_()
+                        mod[-2].weight.data.zero_()
+                elif kind == "768-xxx-768":
+                    mod = nn.Sequential(nn.Linear(width, x, bias=False), nn.GELU(), nn.Dropout(p / 5),
+                                        nn.Linear(x, x, bias=False), nn.GELU(), nn.Dropout(p / 5),
+                                        nn.Linear(x, width, bias=False), nn.Dropout(p))
+                else:  # "linear"
+                    mod = nn.Sequential(nn.Linear(width, width, bias=False), nn.Dropout(p))
+                    mod[0].weight.data = torch.eye(width)
+                setattr(self, f"l{i}_{j}", mod)
+                blk[j] = mod
+            self.layer_blocks.append(blk)
+        self._bf16 = {}
+        self._workspace = None
+
+    # ------------------------------------------------------------------------------------------ native
+    def _check_mode(self):
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("the native adapter has no dropout: call .eval() (training the adapter with "
+                                      "dropout is not implemented by the B200 path)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("gradients through the adapter (dK/dV of the decoder attention) are not "
+                                      "implemented by the B200 path: freeze the adapter (adapter.frozen=1) or run "
+                                      "under torch.no_grad()")
+
+    def _gemm_weight(self, lin):
+        """bf16 copy of a Linear weight for the tensor-core GEMM, rebuilt when the parameter changes."""
+        w = lin.weight
+        key = (w.data_ptr(), w._version, str(w.device))
+        hit = self._bf16.get(id(lin))
+        if hit is None or hit[0] != key:
+            hit = (key, w.detach().to(torch.bfloat16).contiguous())
+            self._bf16[id(lin)] = hit
+        return hit[1]
+
+    def _native_args(self, mod):
+        lins = [m for m in mod if isinstance(m, nn.Linear)]
+        lns = [m for m in mod if isinstance(m, nn.LayerNorm)]
+        w_down = self._gemm_weight(lins[0])
+        w_mid = self._gemm_weight(lins[1]) if len(lins) == 3 else None
+        w_up = self._gemm_weight(lins[-1]) if len(lins) > 1 else None
+        ln_w = ln_b = None
+        if lns:
+            ln_w, ln_b = lns[0].weight.detach(), lns[0].bias.detach()
+            if ln_w.dtype != torch.float32 or not ln_w.is_contiguous() or not ln_b.is_contiguous():
+                raise _native.NativeError("adapter LayerNorm parameters must be contiguous fp32 tensors")
+        return w_down, w_mid, w_up, ln_w, ln_b
+
+    def _adapt(self, mod, tap, rows, ld, group_rows, group_skip):
+        if tap.device.type != "cuda":
+            raise _native.NativeError("dfdclip_b200 adapter needs CUDA tensors (no CPU fallback)")
+        w_down, w_mid, w_up, ln_w, ln_b = self._native_args(mod)
+        with torch.cuda.device(tap.device):
+            self._workspace = _native.adapter_apply(self.kind, tap, rows, ld, self.width, self.inner, w_down, w_mid,
+                                                    w_up, ln_w, ln_b, group_rows, group_skip, self._workspace)
+
+    def apply_packed(self, qkv, layer_indices, n_frames, seq):
+        """Adapt the K and V column blocks of the packed per-layer buffers ``qkv[layer]`` (bf16 ``[n_frames*seq, 3D]``,
+        row = ``[q | k | v]``) in place. CLS rows are transformed too (per-token structs) or zero-filled in the hidden
+        activations (``nln``); the decoder never reads them."""
+        self._check_mode()
+        d = self.width
+        if seq != self.patches + 1:
+            raise ValueError("adapter built for %d patches per frame, got %d tokens" % (self.patches, seq))
+        for blk, layer in zip(self.layer_blocks, layer_indices):
+            buf = qkv[layer]
+            if buf.dtype != torch.bfloat16 or buf.dim() != 2 or buf.shape[1] != 3 * d or buf.stride(1) != 1:
+                raise ValueError("qkv[%d] must be a packed bf16 [rows, %d] buffer" % (layer, 3 * d))
+            for col, name in ((1, "k"), (2, "v")):
+                self._adapt(blk[name], buf[:n_frames * seq, col * d:], n_frames * seq, buf.stride(0), seq, 1)
+        return qkv
+
+    def forward(self, kvs):
+        """Generic entry with the reference's signature (:921-935): ``kvs`` = list of ``{k, v: [B,T,P,H,dh]}``.
+        Each tensor is repacked to a contiguous bf16 ``[B*T*P, D]`` matrix, adapted in place by the native kernels
+        and returned in the reference's shape."""
+        self._check_mode()
+        b, t, p, h, dh = kvs[0]["k"].shape
+        for i in range(len(kvs)):
+            for name in list(kvs[i].keys()):
+                flat = kvs[i][name].detach().to(torch.bfloat16).reshape(b * t * p, h * dh).contiguous()
+                if flat.data_ptr() == kvs[i][name].data_ptr():
+                    flat = flat.clone()  # never modify the caller's tensor (the reference returns new tensors)
+                self._adapt(self.layer_blocks[i][name], flat, b * t * p, h * dh, p, 0)
+                kvs[i][name] = flat.view(b, t, p, h, dh)
+        return kvs
+
+
 class Detector(nn.Module):
     """Deepfake video detector: frozen CLIP ViT frame encoder -> per-layer K/V taps -> temporal decoder
     (reference :394-780). Same constructor and methods as the reference class."""
@@ -312,8 +454,8 @@ class Detector(nn.Module):
         if config.foundation != "clip":
             raise NotImplementedError("foundation=%r: only the CLIP backbone is implemented on the B200 path" %
                                       (config.foundation,))
-        if config.adapter.type != "none":
-            raise NotImplementedError("adapter.type=%r is not implemented by the B200 path" % (config.adapter.type,))
+        if config.adapter.type not in ("none", "normal", "pretrain"):
+            raise NotImplementedError("adapter.type=%r" % (config.adapter.type,))
         if len(config.train_mode) > 0:
             raise NotImplementedError("train_mode %s is not implemented by the B200 path" % (list(config.train_mode),))
         if accelerator is not None and hasattr(accelerator, "main_process_first"):
@@ -341,19 +483,29 @@ class Detector(nn.Module):
         else:
             self.layer_indices = list(config.decode_indices)
         self.decoder = Decoder(self, config, num_frames)
-        self.adapter = None
+        if config.adapter.type == "none":
+            self.adapter = None
+        else:
+            self.adapter = CompInvAdapter(config, self, num_frames=num_frames)
+            if config.adapter.type == "pretrain":  # reference :473-481
+                data = torch.load(config.adapter.path, map_location="cpu")
+                data = {".".join(k.split(".")[1:]): v for k, v in data.items() if "adapter" in k}
+                self.adapter.load_state_dict(data)
+                if config.adapter.frozen:
+                    self.adapter = disable_gradients(self.adapter)
         self.transform = self._transform(self.encoder.input_resolution)
 
     # --------------------------------------------------------------------------------------------- predict
     def predict(self, x, m, with_video_features=False, with_adapt_features=False, train=False):
         """x fp32 [B,T,3,R,R] (normalised frames), m bool [B,T] -> ``(task_logits, features)`` with
         ``task_logits[i] = 5 * l / (||l||_2 + 1e-10)`` (reference :498-566)."""
-        if with_adapt_features:
+        if with_adapt_features and self.adapter is None:
             raise Exception("cannot return adaptive features without an adapter")
         b, t = x.shape[:2]
         with torch.no_grad():
             qkv, _ = self.encoder.encode(x.flatten(0, 1), keep_layers=self.layer_indices)
-        return self.predict_from_taps(qkv, m, b, t, with_video_features=with_video_features, train=train)
+        return self.predict_from_taps(qkv, m, b, t, with_video_features=with_video_features,
+                                      with_adapt_features=with_adapt_features, train=train)
 
     def taps_from_qkv(self, qkv, b, t):
         """Views of the packed per-layer QKV buffers as the decoder's ``[{k, v: [B,T,P,H,64]}]`` list: CLS token
@@ -365,18 +517,23 @@ class Detector(nn.Module):
             kvs.append(dict(k=view[:, :, 1:, 1], v=view[:, :, 1:, 2]))
         return kvs
 
-    def predict_from_taps(self, qkv, m, b, t, with_video_features=False, train=False):
-        """Second half of ``predict``: decoder + logit normalisation on already-encoded taps (``qkv[layer]`` =
-        packed bf16 ``[B*T*L, 3D]`` buffers from ``encoder.encode``)."""
+    def predict_from_taps(self, qkv, m, b, t, with_video_features=False, with_adapt_features=False, train=False):
+        """Second half of ``predict``: adapter (in place on the taps), decoder and logit normalisation on
+        already-encoded taps (``qkv[layer]`` = packed bf16 ``[B*T*L, 3D]`` buffers from ``encoder.encode``)."""
+        if self.adapter is not None:
+            self.adapter.apply_packed(qkv, self.layer_indices, b * t, self.encoder.tokens_per_frame)  # :546-547
         kvs = self.taps_from_qkv(qkv, b, t)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()):
-            # training step (or any caller that wants decoder gradients): differentiable decoder
+        if (torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters())) or \
+                (self.decoder.training and self.decoder.dropout > 0):
+            # training step (or any caller that wants decoder gradients, or active dropout): differentiable decoder
             task_logits, video_features = self.decoder.run_autograd(kvs, m, logit_scale=5.0)
         else:
             task_logits, video_features = self.decoder.run(kvs, m, logit_scale=5.0)
         features = {}
         if with_video_features:
             features["video"] = video_features
+        if with_adapt_features:
+            features["adapt"] = [{n: kv[n].float() for n in ("k", "v")} for kv in kvs]
         return task_logits, features
 
     def forward(self, x, y, m, comp=None, speed=None, train=False, single_task=None, *args, **kargs):

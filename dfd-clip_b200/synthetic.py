@@ -140,13 +140,59 @@ def decoder_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, visua
     return sd
 
 
-def detector_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0):
-    """Full ``Detector.state_dict()`` (encoder.* + decoder.*), the on-disk format of ``*_weights.pt``
-    (written at main.py:119-129, loaded strictly at inference.py:99)."""
+# adapter.struct.type -> Sequential indices of (first Linear, LayerNorm or None, middle Linear or None, last Linear)
+ADAPTER_LAYOUT = {
+    "768-x-768": (0, 2, None, 4),
+    "legacy-768-x-768": (0, 2, None, 3),
+    "768-x-768-nln": (0, 1, None, 4),
+    "768-x-768-ln": (0, 1, None, 4),
+    "768-x-768-z0": (0, 1, None, 4),
+    "768-xxx-768": (0, None, 3, 6),
+    "linear": (0, None, None, None),
+}
+
+
+def adapter_state_dict(arch, n_taps, struct_type, inner=256, seed=0):
+    """fp32 state dict of a ``CompInvAdapter`` (keys ``l{i}_{k|v}.{idx}.{weight|bias}``, src/models.py:783-919) with
+    random, non-degenerate weights. The up-projection is scaled so that the adapter's contribution is about a
+    quarter of the tap it is added to: the shipped structs start from the identity ("-z0", :856-858) and learn a
+    correction, and a bf16 path cannot hold the north_star logit tolerance against fp32 when a random map as large
+    as the tap itself is stacked on the taps (measured: the reference's own fp32 adapter applied to bf16-rounded
+    taps already misses it at |delta| = 0.65 |tap|)."""
+    d = vit_dims(arch)
+    w = d["width"]
+    patches = (d["image_size"] // d["patch_size"]) ** 2
+    first, ln, mid, last = ADAPTER_LAYOUT[struct_type]
+    sd = OrderedDict()
+    for i in range(n_taps):
+        for j in ("k", "v"):
+            pre = "l%d_%s." % (i, j)
+            if struct_type == "linear":
+                sd[pre + "0.weight"] = torch.eye(w) + _randn(seed, "ad." + pre + "0", (w, w), 0.2 * w ** -0.5)
+                continue
+            sd[pre + "%d.weight" % first] = _randn(seed, "ad." + pre + "down", (inner, w), w ** -0.5)
+            if ln is not None:
+                shape = (patches, inner) if struct_type == "768-x-768-nln" else (inner,)
+                sd[pre + "%d.weight" % ln] = _randn(seed, "ad." + pre + "ln.w", shape, 0.1, 1.0)
+                sd[pre + "%d.bias" % ln] = _randn(seed, "ad." + pre + "ln.b", shape, 0.1)
+            if mid is not None:
+                sd[pre + "%d.weight" % mid] = _randn(seed, "ad." + pre + "mid", (inner, inner), 1.5 * inner ** -0.5)
+            sd[pre + "%d.weight" % last] = _randn(seed, "ad." + pre + "up", (w, inner), 0.4 * inner ** -0.5)
+    return sd
+
+
+def detector_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, adapter=None, adapter_inner=256):
+    """Full ``Detector.state_dict()`` (encoder.* + decoder.* [+ adapter.*]), the on-disk format of ``*_weights.pt``
+    (written at main.py:119-129, loaded strictly at inference.py:99). ``adapter`` = an
+    ``adapter.struct.type`` string adds the CompInvAdapter parameters."""
     visual = visual_state_dict(arch, seed)
     sd = OrderedDict(("encoder." + k, v) for k, v in visual.items())
     for k, v in decoder_state_dict(arch, num_frames, out_dims, taps, seed, visual).items():
         sd["decoder." + k] = v
+    if adapter is not None:
+        n_taps = len(layer_indices(arch) if taps is None else list(taps))
+        for k, v in adapter_state_dict(arch, n_taps, adapter, adapter_inner, seed).items():
+            sd["adapter." + k] = v
     return sd
 
 

@@ -38,7 +38,9 @@ enum {
   DFD_EPI_STORE_BF16 = 0,       /* out_bf16 = acc + bias                     (QKV in_proj,  model.py:186)   */
   DFD_EPI_STORE_BF16_QGELU = 1, /* out_bf16 = quickgelu(acc + bias)          (c_fc + QuickGELU, :166,:209)  */
   DFD_EPI_STORE_F32 = 2,        /* out_f32  = acc + bias                     (conv1 as GEMM, :277)          */
-  DFD_EPI_ADD_F32 = 3           /* out_f32 += acc + bias  (in-place residual, out_proj/c_proj :222-223)     */
+  DFD_EPI_ADD_F32 = 3,          /* out_f32 += acc + bias  (in-place residual, out_proj/c_proj :222-223)     */
+  DFD_EPI_ADD_BF16 = 4,         /* out_bf16 += acc + bias (in-place adapter residual, src/models.py:931)    */
+  DFD_EPI_STORE_BF16_GELU = 5   /* out_bf16 = gelu_erf(acc + bias)           (nn.GELU, src/models.py:893)   */
 };
 
 typedef struct dfd_ctx dfd_ctx;
@@ -187,6 +189,36 @@ int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, in
 int dfd_decoder_attention(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                           int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
                           int T, int P, int H, float* mix, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * CompInvAdapter on the tapped K/V (src/models.py:783-940; called from Detector.predict :546-547): a bottleneck
+ * per tapped layer and per {k, v}, applied IN PLACE to a bf16 tap (residual structs) before the decoder reads it.
+ * ---------------------------------------------------------------------------------------------------- */
+enum {
+  DFD_ADAPTER_GELU_LN = 0, /* "768-x-768", "legacy-768-x-768": Linear, GELU, LayerNorm(x), Linear   (:797-818) */
+  DFD_ADAPTER_LN_GELU = 1, /* "768-x-768-ln", "768-x-768-z0":  Linear, LayerNorm(x), GELU, Linear   (:835-861) */
+  DFD_ADAPTER_NLN = 2,     /* "768-x-768-nln": Linear, LayerNorm((patches, x)), GELU, Linear        (:819-834) */
+  DFD_ADAPTER_XXX = 3,     /* "768-xxx-768":   Linear, GELU, Linear, GELU, Linear                   (:881-899) */
+  DFD_ADAPTER_LINEAR = 4   /* "linear":        Linear(D, D), no residual                            (:900-917) */
+};
+
+typedef struct {
+  const void* w_down;     /* bf16 [inner, D]   Sequential[0].weight   ([D, D] for DFD_ADAPTER_LINEAR) */
+  const void* w_mid;      /* bf16 [inner, inner], DFD_ADAPTER_XXX only, else NULL */
+  const void* w_up;       /* bf16 [D, inner]   last Linear.weight */
+  const float* ln_weight; /* fp32 [inner]; [group_rows - group_skip, inner] for DFD_ADAPTER_NLN */
+  const float* ln_bias;
+} dfd_adapter_weights;
+
+size_t dfd_adapter_workspace_bytes(int type, int D, int inner, int64_t rows);
+
+/* kv: bf16 [rows, D] with row pitch `ld` elements (a K or V column slice of a packed QKV buffer: ld = 3D), updated
+ * in place: kv += up(act(down(kv))) (kv = down(kv) for DFD_ADAPTER_LINEAR). inner in {256, 512, 768, 1024}.
+ * group_rows / group_skip (DFD_ADAPTER_NLN only): rows per frame and the leading rows of each frame that take no
+ * part in the joint normalisation (L and 1 for the packed encoder layout with its CLS row; P and 0 otherwise). */
+int dfd_adapter_apply(dfd_ctx* ctx, int type, int D, int inner, const dfd_adapter_weights* w, void* kv, int64_t ld,
+                      int64_t rows, int group_rows, int group_skip, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Training step (config C5): the encoder is frozen, so only the decoder needs gradients. The decoder attention is

@@ -123,18 +123,57 @@ def decoder_forward(sd, kvs, m, out_dims, prefix="decoder."):
     return logits, feat, blocks
 
 
+# adapter.struct.type -> Sequential indices of (first Linear, LayerNorm or None, middle Linear or None, last Linear)
+_ADAPTER_LAYOUT = {
+    "768-x-768": (0, 2, None, 4), "legacy-768-x-768": (0, 2, None, 3), "768-x-768-nln": (0, 1, None, 4),
+    "768-x-768-ln": (0, 1, None, 4), "768-x-768-z0": (0, 1, None, 4), "768-xxx-768": (0, None, 3, 6),
+    "linear": (0, None, None, None),
+}
+
+
+def adapter_forward(sd, kvs, struct_type, prefix="adapter."):
+    """CompInvAdapter.forward (src/models.py:921-935) in eval mode (every Dropout is the identity) for the
+    Sequential layouts of :797-917. kvs: list of {k, v: [B,T,P,H,dh]}; returns the adapted list (new tensors)."""
+    first, ln, mid, last = _ADAPTER_LAYOUT[struct_type]
+    b, t, p, h, d = kvs[0]["k"].shape
+    out = []
+    for i, kv in enumerate(kvs):
+        new = {}
+        for name in ("k", "v"):
+            pre = "%sl%d_%s." % (prefix, i, name)
+            x = kv[name].float().reshape(b, t, p, h * d)                 # :926 view((b, t, p, -1))
+            y = F.linear(x, sd[pre + "%d.weight" % first])
+            if struct_type in ("768-x-768", "legacy-768-x-768"):          # Linear, GELU, LayerNorm(x), Linear
+                y = F.layer_norm(F.gelu(y), (y.shape[-1],), sd[pre + "%d.weight" % ln], sd[pre + "%d.bias" % ln], 1e-5)
+            elif struct_type in ("768-x-768-ln", "768-x-768-z0"):         # Linear, LayerNorm(x), GELU, Linear
+                y = F.gelu(F.layer_norm(y, (y.shape[-1],), sd[pre + "%d.weight" % ln], sd[pre + "%d.bias" % ln], 1e-5))
+            elif struct_type == "768-x-768-nln":                          # Linear, LayerNorm((P, x)), GELU, Linear
+                y = F.gelu(F.layer_norm(y, tuple(y.shape[-2:]), sd[pre + "%d.weight" % ln], sd[pre + "%d.bias" % ln],
+                                        1e-5))
+            elif struct_type == "768-xxx-768":                            # Linear, GELU, Linear, GELU, Linear
+                y = F.gelu(F.linear(F.gelu(y), sd[pre + "%d.weight" % mid]))
+            if last is not None:
+                y = F.linear(y, sd[pre + "%d.weight" % last])
+            y = y.view(b, t, p, h, d)
+            new[name] = kv[name].float() + y if struct_type != "linear" else y   # :930-933
+        out.append(new)
+    return out
+
+
 def normalise_logits(task_logits):
     # Detector.predict, src/models.py:551-553
     return [5 * l / (torch.norm(l, dim=-1, keepdim=True) + 1e-10) for l in task_logits]
 
 
-def detector_predict(sd, x, m, layer_indices, out_dims, return_taps=False):
-    """Detector.predict (src/models.py:498-566, no adapter, no patch mask).
+def detector_predict(sd, x, m, layer_indices, out_dims, return_taps=False, adapter=None):
+    """Detector.predict (src/models.py:498-566, no patch mask; ``adapter`` = adapter.struct.type or None).
     x: fp32 [B,T,3,R,R]; m: bool [B,T]. Returns (normalised task logits, video feature[, taps])."""
     b, t = x.shape[:2]
     run = max(layer_indices) + 1
     enc = encoder_forward(sd, x.flatten(0, 1), num_layers=run)                                   # :503
     kvs = [{n: enc[i][n][:, 1:].unflatten(0, (b, t)) for n in ("k", "v")} for i in layer_indices]  # :505-509
+    if adapter is not None:
+        kvs = adapter_forward(sd, kvs, adapter)                                                  # :546-547
     logits, feat, _ = decoder_forward(sd, kvs, m, out_dims)                                      # :549
     logits = normalise_logits(logits)
     if return_taps:

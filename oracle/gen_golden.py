@@ -29,12 +29,22 @@ sys.path.insert(0, ROOT)
 
 from dfdclip_b200 import synthetic  # noqa: E402  (weights/clips factory shared with tests and bench)
 
-# name -> (arch, T, B, full K/V stored?)
+# name -> (arch, T, B, full K/V stored?[, adapter.struct.type])
 CASES = {
     "tiny": ("tiny-256x4", 4, 3, True),
     "small": ("small-512x6", 3, 2, False),
     "vitb16": ("ViT-B/16", 8, 2, False),
     "vitl14": ("ViT-L/14", 4, 1, False),
+    # CompInvAdapter (src/models.py:783-940), one case per Sequential layout
+    "tiny_ad_x": ("tiny-256x4", 4, 3, True, "768-x-768"),
+    "tiny_ad_legacy": ("tiny-256x4", 4, 3, True, "legacy-768-x-768"),
+    "tiny_ad_nln": ("tiny-256x4", 4, 3, True, "768-x-768-nln"),
+    "tiny_ad_ln": ("tiny-256x4", 4, 3, True, "768-x-768-ln"),
+    "tiny_ad_z0": ("tiny-256x4", 4, 3, True, "768-x-768-z0"),
+    "tiny_ad_xxx": ("tiny-256x4", 4, 3, True, "768-xxx-768"),
+    "tiny_ad_linear": ("tiny-256x4", 4, 3, True, "linear"),
+    "vitb16_ad_nln": ("ViT-B/16", 8, 2, False, "768-x-768-nln"),
+    "vitb16_ad_z0": ("ViT-B/16", 8, 2, False, "768-x-768-z0"),
 }
 N_SAMPLES = 4096
 
@@ -91,7 +101,7 @@ def sample_indices(numel, seed):
     return torch.randint(0, numel, (min(N_SAMPLES, numel),), generator=g)
 
 
-def run_case(name, arch, num_frames, batch, full):
+def run_case(name, arch, num_frames, batch, full, adapter=None):
     from src.models import Detector  # the reference's own class
 
     dims = synthetic.vit_dims(arch)
@@ -103,11 +113,17 @@ def run_case(name, arch, num_frames, batch, full):
     cfg.architecture = ckpt
     cfg.out_dim = [2]
     cfg.losses = ["auc_roc"]
+    if adapter is not None:
+        from yacs.config import CfgNode
+        cfg.adapter.type = "normal"
+        cfg.adapter.frozen = 0
+        cfg.adapter.struct = CfgNode({"type": adapter, "x": 256})
     torch.manual_seed(1)
     det = Detector(cfg, num_frames, FakeAccelerator())
     os.remove(ckpt)
 
-    sd = synthetic.detector_state_dict(arch, num_frames, out_dims=(2,), taps=det.layer_indices, seed=0)
+    sd = synthetic.detector_state_dict(arch, num_frames, out_dims=(2,), taps=det.layer_indices, seed=0,
+                                       adapter=adapter, adapter_inner=256)
     # the encoder built by the reference's clip.load/build_model must equal the synthetic fp32 values exactly
     # (they are fp16-representable where build_model rounds)
     for k, v in det.encoder.state_dict().items():
@@ -120,7 +136,7 @@ def run_case(name, arch, num_frames, batch, full):
     labels = torch.arange(batch) % 2
     with torch.no_grad():
         taps = det.encoder(x.flatten(0, 1), with_out=True, with_q=True)
-        logits, feats = det.predict(x, m, with_video_features=True)
+        logits, feats = det.predict(x, m, with_video_features=True, with_adapt_features=adapter is not None)
         losses, logits2 = det(x, [labels], m, single_task=0)
     assert torch.equal(logits[0], logits2[0])
 
@@ -130,7 +146,25 @@ def run_case(name, arch, num_frames, batch, full):
         "logits": logits[0].numpy(), "video_feature": feats["video"].numpy(), "losses": losses[0].numpy(),
         "pred_labels": logits[0].argmax(-1).numpy(),
     }
+    if adapter is not None:
+        out["adapter"] = np.array(adapter)
+        # adapted taps as the decoder received them: predict's kvs after the adapter AND after Decoder.forward's
+        # in-place list edits (positional embedding added, (t, p) flattened — src/models.py:326-334)
+        for i, kv in enumerate(feats["adapt"]):
+            for key in ("k", "v"):
+                t = kv[key].contiguous().float()
+                if det.decoder.positional_embedding is not None:
+                    t = (t.view(batch, num_frames, -1, *t.shape[-2:]) - det.decoder.positional_embedding).contiguous()
+                out["norm_adapt_%s_%d" % (key, i)] = np.array(t.norm().item(), dtype=np.float64)
+                if full:
+                    out["adapt_%s_%d" % (key, i)] = t.detach().numpy()
+                else:
+                    idx = sample_indices(t.numel(), seed=5000 + 10 * i + (key == "v"))
+                    out["idx_adapt_%s_%d" % (key, i)] = idx.numpy()
+                    out["val_adapt_%s_%d" % (key, i)] = t.flatten()[idx].detach().numpy()
     for i, a in enumerate(taps):
+        if adapter is not None:
+            break  # the raw taps are pinned by the adapter-less cases
         for key in ("q", "k", "v", "out"):
             t = a[key].contiguous().float()
             out["norm_%s_%d" % (key, i)] = np.array(t.norm().item(), dtype=np.float64)
@@ -153,10 +187,10 @@ def main(argv):
     sys.path.insert(0, REFERENCE)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    for name, (arch, t, b, full) in CASES.items():
+    for name, case in CASES.items():
         if len(argv) > 1 and name not in argv[1:]:
             continue
-        run_case(name, arch, t, b, full)
+        run_case(name, *case)
 
 
 if __name__ == "__main__":

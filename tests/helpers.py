@@ -36,7 +36,9 @@ def golden_inputs(g):
     """The exact (state_dict, clips, mask) the golden generator fed the reference."""
     from dfdclip_b200 import synthetic
     dims = synthetic.vit_dims(g["arch"])
-    sd = synthetic.detector_state_dict(g["arch"], g["num_frames"], out_dims=(2,), taps=g["layer_indices"], seed=0)
+    adapter = str(g["adapter"]) if "adapter" in g else None
+    sd = synthetic.detector_state_dict(g["arch"], g["num_frames"], out_dims=(2,), taps=g["layer_indices"], seed=0,
+                                       adapter=adapter, adapter_inner=256)
     x, m = synthetic.make_clips(g["batch"], g["num_frames"], dims["image_size"], seed=7)
     assert np.array_equal(m.numpy(), g["mask"])
     return sd, x, m

@@ -10,6 +10,7 @@ import torch
 import torch.multiprocessing as mp
 
 from helpers import ROOT, load_oracle
+from dfdclip_b200.config import CN
 
 
 # ------------------------------------------------------------------------------------------ C ABI
@@ -110,9 +111,12 @@ def test_index_decode_mode_and_unsupported_knobs():
     from dfdclip_b200.models import Detector
     for mutate in (lambda c: c.op_mode.__setitem__("attn_mode", "frame"),
                    lambda c: c.op_mode.__setitem__("aug_query", 1),
-                   lambda c: c.adapter.__setitem__("type", "normal"),
+                   lambda c: c.adapter.__setitem__("type", "lora"),
+                   lambda c: (c.adapter.__setitem__("type", "normal"),
+                              c.adapter.__setitem__("struct", CN({"type": "768-bn", "x": 256}))),
+                   lambda c: (c.adapter.__setitem__("type", "normal"),
+                              c.adapter.__setitem__("struct", CN({"type": "768-x-768-z0", "x": 100}))),
                    lambda c: c.__setitem__("foundation", "dinov2"),
-                   lambda c: c.__setitem__("dropout", 0.1),
                    lambda c: c.train_mode.__setitem__("temporal", "ranking")):
         cfg = Detector.get_default_config()
         cfg.architecture = "synthetic:tiny-256x4"

@@ -35,6 +35,39 @@ def test_oracle_matches_reference_golden(oracle, case):
     assert np.abs(losses[0].numpy() - g["losses"]).max() < 1e-4
 
 
+ADAPTER_CASES = ["tiny_ad_x", "tiny_ad_legacy", "tiny_ad_nln", "tiny_ad_ln", "tiny_ad_z0", "tiny_ad_xxx",
+                 "tiny_ad_linear", "vitb16_ad_nln", "vitb16_ad_z0"]
+
+
+@pytest.mark.parametrize("case", ADAPTER_CASES)
+def test_oracle_adapter_matches_reference_golden(oracle, case):
+    """CompInvAdapter (src/models.py:783-940) between the taps and the decoder, every Sequential layout."""
+    g = load_golden(case)
+    sd, x, m = golden_inputs(g)
+    struct = str(g["adapter"])
+    with torch.no_grad():
+        logits, feat, raw = oracle.detector_predict(sd, x, m, g["layer_indices"], (2,), return_taps=True,
+                                                    adapter=struct)
+    assert np.abs(logits[0].numpy() - g["logits"]).max() < 1e-4
+    assert np.abs(feat.numpy() - g["video_feature"]).max() < 2e-4
+    assert np.array_equal(logits[0].argmax(-1).numpy(), g["pred_labels"])
+    for i, kv in enumerate(raw):  # return_taps hands back the adapted taps the decoder consumed
+        for key in ("k", "v"):
+            ref, got = golden_tensor(g, "adapt_" + key, i, kv[key])
+            assert (got - ref).abs().max().item() <= 2e-4 * max(ref.abs().max().item(), 1.0), (case, i, key)
+
+
+def test_z0_adapter_is_identity_at_init(oracle):
+    """'768-x-768-z0' zero-initialises the LayerNorm weight and the up projection (src/models.py:856-858):
+    a freshly constructed adapter leaves the taps unchanged."""
+    from dfdclip_b200 import synthetic
+    sd = synthetic.adapter_state_dict("tiny-256x4", 1, "768-x-768-z0", 256, seed=0)
+    sd = {"adapter." + k: (torch.zeros_like(v) if k.endswith(("1.weight", "4.weight")) else v) for k, v in sd.items()}
+    kv = [dict(k=torch.randn(2, 3, 4, 4, 64), v=torch.randn(2, 3, 4, 4, 64))]
+    out = oracle.adapter_forward(sd, kv, "768-x-768-z0")
+    assert torch.equal(out[0]["k"], kv[0]["k"]) and torch.equal(out[0]["v"], kv[0]["v"])
+
+
 def test_logits_have_norm_five(oracle):
     g = load_golden("tiny")
     assert np.allclose(np.linalg.norm(g["logits"], axis=-1), 5.0, atol=1e-4)

@@ -147,7 +147,7 @@ def test_unsupported_configs_raise(cuda_device):
         Detector(cfg, 4, None)
     cfg = Detector.get_default_config()
     cfg.architecture = "synthetic:tiny-256x4"
-    cfg.adapter.type = "normal"
+    cfg.adapter.type = "lora"
     with pytest.raises(NotImplementedError):
         Detector(cfg, 4, None)
 
