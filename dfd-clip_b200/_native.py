@@ -25,7 +25,8 @@ EXPORTS = (
     "dfd_decoder_workspace_bytes", "dfd_decoder_forward", "dfd_project_logits", "dfd_decoder_attention",
     "dfd_timing_enable", "dfd_timing_read", "dfd_timing_num_tags", "dfd_timing_tag_name",
     "dfd_decoder_attention_workspace_bytes", "dfd_decoder_attention_train", "dfd_decoder_attention_backward",
-    "dfd_adapter_workspace_bytes", "dfd_adapter_apply",
+    "dfd_adapter_workspace_bytes", "dfd_adapter_apply", "dfd_ema_frames",
+    "dfd_decoder_attention_modes_workspace_bytes", "dfd_decoder_attention_modes",
 )
 
 
@@ -54,7 +55,11 @@ class DecoderWeights(ctypes.Structure):
         "ln_post_bias")] + [
         (n, _PP) for n in (
             "ln_1_weight", "ln_1_bias", "in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias",
-            "ln_2_weight", "ln_2_bias", "c_fc_weight", "c_fc_bias", "c_proj_weight", "c_proj_bias")]
+            "ln_2_weight", "ln_2_bias", "c_fc_weight", "c_fc_bias", "c_proj_weight", "c_proj_bias",
+            "augment_query")] + [("attn_mode", c_int)]
+
+
+ATTN_FRAME, ATTN_TEMPORAL = 1, 2
 
 
 class KvTaps(ctypes.Structure):
@@ -99,7 +104,7 @@ def load_library():
                                                  c_void_p, c_void_p]
         lib.dfd_encoder_forward.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p, c_int, c_int,
                                             c_int, _PP, _PP, c_void_p, c_size_t, c_void_p]
-        lib.dfd_decoder_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        lib.dfd_decoder_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
         lib.dfd_decoder_workspace_bytes.restype = c_size_t
         lib.dfd_decoder_forward.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
                                             ctypes.POINTER(KvTaps), c_void_p, c_int, c_int, c_int, c_void_p,
@@ -121,6 +126,12 @@ def load_library():
         lib.dfd_adapter_workspace_bytes.restype = c_size_t
         lib.dfd_adapter_apply.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdapterWeights), c_void_p,
                                           c_int64, c_int64, c_int, c_int, c_void_p, c_size_t, c_void_p]
+        lib.dfd_decoder_attention_modes_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        lib.dfd_decoder_attention_modes_workspace_bytes.restype = c_size_t
+        lib.dfd_decoder_attention_modes.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                                    c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                                    c_void_p, c_size_t, c_void_p]
+        lib.dfd_ema_frames.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_void_p]
         lib.dfd_timing_enable.argtypes = [c_void_p, c_int]
         lib.dfd_timing_read.argtypes = [c_void_p, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_int)]
         lib.dfd_timing_tag_name.argtypes = [c_int]
@@ -252,6 +263,21 @@ def decoder_attention(qs, k, v, pos_emb, mask):
     return mix
 
 
+def decoder_attention_modes(qs, k, v, pos_emb, mask, attn_mode):
+    """decoder_attention for op_mode.attn_mode: attn_mode = ATTN_FRAME | ATTN_TEMPORAL bit set."""
+    b, t, p, h = _check_kv(k, v)
+    lib = load_library()
+    m8 = mask.to(torch.uint8).contiguous()
+    mix = torch.empty((b, h * 64), dtype=torch.float32, device=k.device)
+    nbytes = lib.dfd_decoder_attention_modes_workspace_bytes(b, t, p, h)
+    ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=k.device)
+    check(lib.dfd_decoder_attention_modes(
+        ctx(k.device), ptr(qs.contiguous()), ptr(k), ptr(v), k.stride(0), k.stride(1), k.stride(2),
+        ptr(None if pos_emb is None else pos_emb.contiguous()), ptr(m8), b, t, p, h, attn_mode, ptr(mix), ptr(ws),
+        nbytes, stream_ptr(k.device)))
+    return mix
+
+
 def project_logits(feature, proj, scale=5.0):
     b, d = feature.shape
     o = proj.shape[1]
@@ -315,3 +341,17 @@ def adapter_apply(kind, kv, rows, ld, width, inner, w_down, w_mid, w_up, ln_weig
     check(lib.dfd_adapter_apply(ctx(dev), kind, width, inner, ctypes.byref(w), ptr(kv), ld, rows, group_rows,
                                 group_skip, ptr(workspace), workspace.numel(), stream_ptr(dev)))
     return workspace
+
+
+def ema_frames(x, ratio):
+    """op_mode.ema_frame: x fp32 [B,T,...] -> [B,1,...], the reference's EMA recurrence over the frame axis."""
+    assert x.dtype == torch.float32 and x.dim() >= 3
+    x = x.contiguous()
+    b, t = x.shape[:2]
+    out = torch.empty((b, 1) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    elems = 1
+    for n in x.shape[2:]:
+        elems *= int(n)
+    check(load_library().dfd_ema_frames(ctx(x.device), ptr(x), ptr(out), b, t, elems, float(ratio),
+                                        stream_ptr(x.device)))
+    return out

@@ -73,6 +73,12 @@ int decoder_attention_stream(const dfd_ctx* ctx, const float* qs, const void* k,
 
 size_t dec_attn_workspace_bytes(int B, int T, int H) { return dec_attn_stream_workspace_bytes(B, T, H); }
 
+size_t dec_attn_modes_workspace_bytes(int B, int T, int P, int H);
+int decoder_attention_modes(const dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
+                            int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B, int T,
+                            int P, int H, int attn_mode, float* mix, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream);
+
 int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                       int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B, int T, int P,
                       int H, float* mix, void* workspace, size_t workspace_bytes, cudaStream_t stream,
@@ -243,6 +249,45 @@ __global__ void scatter_block_out_kernel(const float* __restrict__ src, float* _
   if (i < B * D) dst[(static_cast<int64_t>(i / D) * n_slots + slot) * D + (i % D)] = src[i];
 }
 
+// x[b, :] += vec[:]   (op_mode.aug_query, models.py:265-267)
+__global__ void add_row_vector_kernel(float* __restrict__ x, const float* __restrict__ vec, int B, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * D) x[i] += vec[i % D];
+}
+
+// op_mode.ema_frame (models.py:572-578): the reference's recurrence, same operation order (no FMA contraction)
+__global__ void __launch_bounds__(256)
+ema_frames_kernel(const float4* __restrict__ x, float4* __restrict__ out, int T, int64_t frame_vec4, float ratio,
+                  int64_t total_vec4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_vec4) return;
+  const int64_t b = i / frame_vec4, e = i % frame_vec4;
+  const float4* src = x + b * T * frame_vec4 + e;
+  const float keep = 1.0f - ratio;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < T; ++t) {
+    const float4 v = __ldg(src + t * frame_vec4);
+    acc.x = __fadd_rn(__fmul_rn(acc.x, ratio), __fmul_rn(v.x, keep));
+    acc.y = __fadd_rn(__fmul_rn(acc.y, ratio), __fmul_rn(v.y, keep));
+    acc.z = __fadd_rn(__fmul_rn(acc.z, ratio), __fmul_rn(v.z, keep));
+    acc.w = __fadd_rn(__fmul_rn(acc.w, ratio), __fmul_rn(v.w, keep));
+  }
+  out[i] = acc;
+}
+
+int ema_frames(const float* x, float* out, int B, int T, int64_t frame_elems, float ratio, cudaStream_t stream) {
+  DFD_CHECK_ARG(B >= 0 && T > 0 && frame_elems > 0 && frame_elems % 4 == 0, "ema_frames: bad shape");
+  if (B == 0) return 0;
+  DFD_CHECK_ARG(x && out, "ema_frames: null pointer");
+  DFD_CHECK_ARG((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+                "ema_frames: buffers must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * (frame_elems / 4);
+  ema_frames_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), T, frame_elems / 4, ratio, total);
+  DFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------- projection + logit scaling
 // One CTA per clip: l = feature[b] @ proj[D,O]; logits = scale * l / (||l||_2 + 1e-10)  (models.py:359, 551-553)
 __global__ void __launch_bounds__(256)
@@ -288,7 +333,7 @@ struct DecWs {
   size_t total;
 };
 
-static DecWs carve_decoder_ws(void* base, int B, int T, int D, int H) {
+static DecWs carve_decoder_ws(void* base, int B, int T, int P, int D, int H, int attn_mode) {
   auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t off = 0;
@@ -303,7 +348,7 @@ static DecWs carve_decoder_ws(void* base, int B, int T, int D, int H) {
   w.qs = take(sizeof(float) * B * 2 * D);
   w.mix = take(sizeof(float) * B * D);
   w.hid = take(sizeof(float) * B * 4 * D);
-  w.part = take(dec_attn_workspace_bytes(B, T, H));
+  w.part = take(attn_mode ? dec_attn_modes_workspace_bytes(B, T, P, H) : dec_attn_workspace_bytes(B, T, H));
   w.lin = take(linear_workspace_bytes(B, 4 * D));
   w.total = off;
   return w;
@@ -316,7 +361,7 @@ int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_de
   DFD_CHECK_ARG(n_blocks > 0 && B >= 0 && T > 0 && P > 0, "decoder_forward: bad shape");
   if (B == 0) return 0;  // empty batch: nothing to do (buffers of empty tensors are NULL)
   DFD_CHECK_ARG(w && taps && mask && block_out && video_feature, "decoder_forward: null pointer");
-  DecWs ws = carve_decoder_ws(workspace, B, T, D, H);
+  DecWs ws = carve_decoder_ws(workspace, B, T, P, D, H, w->attn_mode);
   if (!workspace || workspace_bytes < ws.total)
     return fail(DFD_ERR_WORKSPACE, "decoder_forward: workspace %zu < %zu bytes", workspace_bytes, ws.total);
   const int nthr = 256, nblk = (B * D + nthr - 1) / nthr;
@@ -337,10 +382,17 @@ int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_de
               layernorm(ws.x, w->ln_1_weight[i], w->ln_1_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
     DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.y, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, ws.qs, B,
                                              2 * D, D, false, ws.lin, stream));
-    DFD_TIMED(DFD_TAG_DEC_ATTN,
-              decoder_attention(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
-                                w->positional_embedding, mask, B, T, P, H, ws.mix, ws.part,
-                                dec_attn_workspace_bytes(B, T, H), stream));
+    if (w->attn_mode) {
+      DFD_TIMED(DFD_TAG_DEC_ATTN,
+                decoder_attention_modes(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t,
+                                        taps->stride_p, w->positional_embedding, mask, B, T, P, H, w->attn_mode, ws.mix,
+                                        ws.part, dec_attn_modes_workspace_bytes(B, T, P, H), stream));
+    } else {
+      DFD_TIMED(DFD_TAG_DEC_ATTN,
+                decoder_attention(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
+                                  w->positional_embedding, mask, B, T, P, H, ws.mix, ws.part,
+                                  dec_attn_workspace_bytes(B, T, H), stream));
+    }
     DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.mix, w->out_proj_weight[i], w->out_proj_bias[i], ws.x, ws.x, B,
                                              D, D, false, ws.lin, stream));
     // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                     (models.py:175)
@@ -353,6 +405,11 @@ int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_de
                                              4 * D, false, ws.lin, stream));
     scatter_block_out_kernel<<<nblk, nthr, 0, stream>>>(ws.x, block_out, B, D, i, n_blocks);
     DFD_CUDA_OK(cudaGetLastError());
+    if (w->augment_query && i + 1 < n_blocks) {  // models.py:265-267 (the recorded block output excludes it)
+      DFD_CHECK_ARG(w->augment_query[i] != nullptr, "decoder_forward: augment_query[%d] is NULL", i);
+      add_row_vector_kernel<<<nblk, nthr, 0, stream>>>(ws.x, w->augment_query[i], B, D);
+      DFD_CUDA_OK(cudaGetLastError());
+    }
   }
   // video_feature = ln_post(x_last)                                  (models.py:340-343)
   DFD_TRY(layernorm(ws.x, w->ln_post_weight, w->ln_post_bias, nullptr, 0, nullptr, video_feature, B, D, stream));
@@ -363,10 +420,10 @@ int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_de
 
 extern "C" {
 
-size_t dfd_decoder_workspace_bytes(int B, int T, int D, int n_blocks) {
+size_t dfd_decoder_workspace_bytes(int B, int T, int P, int D, int n_blocks, int attn_mode) {
   (void)n_blocks;
-  if (B <= 0 || T <= 0 || D <= 0) return 0;
-  return dfd::carve_decoder_ws(nullptr, B, T, D, D / 64).total;
+  if (B <= 0 || T <= 0 || P <= 0 || D <= 0) return 0;
+  return dfd::carve_decoder_ws(nullptr, B, T, P, D, D / 64, attn_mode).total;
 }
 
 int dfd_decoder_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
@@ -383,6 +440,13 @@ int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, in
   dfd::clear_error();
   if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_project_logits: ctx is NULL");
   return dfd::project_logits(feature, proj, B, D, O, scale, logits, static_cast<cudaStream_t>(stream));
+}
+
+int dfd_ema_frames(dfd_ctx* ctx, const float* x, float* out, int B, int T, int64_t frame_elems, float ratio,
+                   void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_ema_frames: ctx is NULL");
+  return dfd::ema_frames(x, out, B, T, frame_elems, ratio, static_cast<cudaStream_t>(stream));
 }
 
 int dfd_decoder_attention(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,

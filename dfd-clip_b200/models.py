@@ -17,7 +17,6 @@ from torch import nn
 from . import _native, clip
 from .config import CN
 
-_UNSUPPORTED_OP_MODES = ("attn_mode", "global_prediction", "aug_query", "ema_frame")
 
 
 def auc_roc(weight=None, label_smoothing=0.0, *args, **kargs):
@@ -95,10 +94,16 @@ class Transformer(nn.Module):
     def __init__(self, width, heads, config, num_frames, layer_indices, reference_layers):
         super().__init__()
         self.width = width
-        self.resblocks = nn.Sequential(*[
-            ResidualAttentionBlock(width, heads, config, num_frames, i, layer_indices, reference_layers)
-            for i in range(len(layer_indices))
-        ])
+        blocks = [ResidualAttentionBlock(width, heads, config, num_frames, i, layer_indices, reference_layers)
+                  for i in range(len(layer_indices))]
+        # op_mode.aug_query (reference :250-255): a learnable vector added to the query between blocks
+        self.augment_query_embeddings = []
+        if "aug_query" in config.op_mode and config.op_mode.aug_query:
+            for i in range(len(layer_indices) - 1):
+                name = f"augment_query_{i}"
+                setattr(self, name, nn.Parameter(torch.zeros(width)))
+                self.augment_query_embeddings.append(getattr(self, name))
+        self.resblocks = nn.Sequential(*blocks)
 
 
 class _DecoderAttentionFn(torch.autograd.Function):
@@ -135,9 +140,16 @@ class Decoder(nn.Module):
         heads = detector.encoder.heads
         self.width, self.heads, self.num_frames = width, heads, num_frames
         self.op_mode = config.op_mode
-        for key in _UNSUPPORTED_OP_MODES:
-            if key in config.op_mode and config.op_mode[key]:
-                raise NotImplementedError("op_mode.%s is not implemented by the B200 path" % key)
+        # op_mode.attn_mode (reference :83, 107-115): "frame", "temporal" or both joined by "+"
+        self.attn_mode = 0
+        if "attn_mode" in config.op_mode and config.op_mode.attn_mode:
+            for part in config.op_mode.attn_mode.split("+"):
+                if part == "frame":
+                    self.attn_mode |= _native.ATTN_FRAME
+                elif part == "temporal":
+                    self.attn_mode |= _native.ATTN_TEMPORAL
+            if self.attn_mode == 0:  # the reference's smax would return sum([]) = 0 for an unknown mode string
+                raise NotImplementedError("op_mode.attn_mode=%r" % (config.op_mode.attn_mode,))
         self.dropout = float(config.dropout)
         scale = width ** -0.5
         self.class_embedding = nn.Parameter(scale * torch.randn(width))
@@ -151,12 +163,22 @@ class Decoder(nn.Module):
                                        reference_layers=detector.encoder.transformer.resblocks)
         self.ln_post = LayerNorm(width)
         self.drop_post = nn.Dropout(config.dropout)
+        self.global_prediction = bool("global_prediction" in config.op_mode and config.op_mode.global_prediction)
         self.task_projections = []
         for i, output_dim in enumerate(config.out_dim):
-            name = f"proj{i}x{output_dim}"
-            setattr(self, name, nn.Parameter(scale * torch.randn(width, output_dim)))
-            self.task_projections.append([getattr(self, name)])
+            mats = []
+            if self.global_prediction:  # one projection per tapped layer (reference :309-313)
+                for l in detector.layer_indices:
+                    name = f"proj{i}x{output_dim}_L{l}"
+                    setattr(self, name, nn.Parameter(scale * torch.randn(width, output_dim)))
+                    mats.append(getattr(self, name))
+            else:
+                name = f"proj{i}x{output_dim}"
+                setattr(self, name, nn.Parameter(scale * torch.randn(width, output_dim)))
+                mats.append(getattr(self, name))
+            self.task_projections.append(mats)
         self._wcache = None
+        self._gp_cache = {}
         self._workspace = None
 
     # ------------------------------------------------------------------------------------------ native
@@ -189,6 +211,14 @@ class Decoder(nn.Module):
         w.ln_2_weight, w.ln_2_bias = arr(lambda b: b.ln_2.weight), arr(lambda b: b.ln_2.bias)
         w.c_fc_weight, w.c_fc_bias = arr(lambda b: b.mlp.c_fc.weight), arr(lambda b: b.mlp.c_fc.bias)
         w.c_proj_weight, w.c_proj_bias = arr(lambda b: b.mlp.c_proj.weight), arr(lambda b: b.mlp.c_proj.bias)
+        aug = self.transformer.augment_query_embeddings
+        if aug:
+            a = _native.ptr_array(list(aug))
+            keep.append(a)
+            w.augment_query = ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p))
+        else:
+            w.augment_query = None
+        w.attn_mode = self.attn_mode
         self._wcache = (key, w, keep)
         return w
 
@@ -207,16 +237,31 @@ class Decoder(nn.Module):
         h, d = self.heads, self.width
         if k0.device.type != "cuda":
             raise _native.NativeError("dfdclip_b200 decoder needs CUDA tensors (no CPU fallback)")
+        if self.attn_mode:
+            raise NotImplementedError("the training step (decoder backward) is implemented for the default "
+                                      "op_mode.attn_mode only")
         x = self.drop_pre(self.ln_pre(self.class_embedding.view(1, d)).expand(b, d))
-        for blk, kv in zip(self.transformer.resblocks, kvs):
+        aug = self.transformer.augment_query_embeddings
+        outs = []
+        for i, (blk, kv) in enumerate(zip(self.transformer.resblocks, kvs)):
             qs = blk.attn.in_proj(blk.ln_1(x)).view(b, h, 128)
             mix = _DecoderAttentionFn.apply(qs, self.positional_embedding, kv["k"].detach(), kv["v"].detach(), m)
             x = x + blk.attn.out_proj(mix)
             x = x + blk.mlp(blk.ln_2(x))
-        video_feature = self.drop_post(self.ln_post(x))
+            outs.append(x)
+            if aug and i + 1 < len(kvs):
+                x = x + aug[i]
+        if self.global_prediction:
+            video_feature = self.drop_post(self.ln_post(torch.stack(outs, dim=1)))  # [B, n_blocks, D] (:340-343)
+        else:
+            video_feature = self.drop_post(self.ln_post(outs[-1]))
         task_logits = []
         for mats in self.task_projections:
-            l = video_feature @ mats[-1]
+            if self.global_prediction:  # weighted sum of the per-layer predictions (:345-357)
+                n = len(mats)
+                l = sum((video_feature[:, j] @ mats[j]) * (j + 1) / ((1 + n) * n / 2) for j in range(n))
+            else:
+                l = video_feature @ mats[-1]
             if logit_scale > 0:
                 l = logit_scale * l / (torch.norm(l, dim=-1, keepdim=True) + 1e-10)
             task_logits.append(l)
@@ -267,7 +312,7 @@ class Decoder(nn.Module):
             raise ValueError("mask shape %s does not match clips [%d, %d]" % (tuple(mask.shape), b, t))
         block_out = torch.empty((b, nb, d), dtype=torch.float32, device=dev)
         video_feature = torch.empty((b, d), dtype=torch.float32, device=dev)
-        ws_bytes = lib.dfd_decoder_workspace_bytes(b, t, d, nb)
+        ws_bytes = lib.dfd_decoder_workspace_bytes(b, t, p, d, nb, self.attn_mode)
         if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
             self._workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
@@ -275,10 +320,30 @@ class Decoder(nn.Module):
                 _native.ctx(dev), d, self.heads, nb, ctypes.byref(w), ctypes.byref(taps), _native.ptr(mask), b, t, p,
                 _native.ptr(block_out), _native.ptr(video_feature), _native.ptr(self._workspace), ws_bytes,
                 _native.stream_ptr(dev)))
-            task_logits = [_native.project_logits(video_feature, mats[-1].detach(), scale=logit_scale)
-                           for mats in self.task_projections]
+            if self.global_prediction:
+                # ln_post over every block output, then sum_j c_j (f_j @ P_j) = [f_0 | f_1 | ...] @ vstack(c_j P_j)
+                video_feature = _native.layernorm(block_out.view(b * nb, d), self.ln_post.weight.detach(),
+                                                  self.ln_post.bias.detach(), out_dtype=torch.float32).view(b, nb, d)
+                task_logits = [_native.project_logits(video_feature.view(b, nb * d), self._stacked_projection(i),
+                                                      scale=logit_scale) for i in range(len(self.task_projections))]
+            else:
+                task_logits = [_native.project_logits(video_feature, mats[-1].detach(), scale=logit_scale)
+                               for mats in self.task_projections]
         self.last_block_outputs = block_out
         return task_logits, video_feature
+
+    def _stacked_projection(self, task):
+        """``vstack_j (j+1)/(n(n+1)/2) * proj_L{j}`` ([n*D, out]) for op_mode.global_prediction (reference :345-357),
+        rebuilt when a projection parameter changes."""
+        mats = self.task_projections[task]
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in mats)
+        hit = self._gp_cache.get(task)
+        if hit is None or hit[0] != key:
+            n = len(mats)
+            stacked = torch.cat([p.detach().float() * ((j + 1) / ((1 + n) * n / 2)) for j, p in enumerate(mats)], dim=0)
+            hit = (key, stacked.contiguous())
+            self._gp_cache[task] = hit
+        return hit[1]
 
 
 class CompInvAdapter(nn.Module):
@@ -456,8 +521,14 @@ class Detector(nn.Module):
                                       (config.foundation,))
         if config.adapter.type not in ("none", "normal", "pretrain"):
             raise NotImplementedError("adapter.type=%r" % (config.adapter.type,))
-        if len(config.train_mode) > 0:
-            raise NotImplementedError("train_mode %s is not implemented by the B200 path" % (list(config.train_mode),))
+        for key in config.train_mode:
+            if key != "patch_mask":  # "temporal" (ranking loss) and "compression" (adapter losses): trainer-side extras
+                raise NotImplementedError("train_mode.%s is not implemented by the B200 path" % (key,))
+        if "ema_frame" in config.op_mode and config.op_mode.ema_frame and \
+                "temporal_position" in config.op_mode and config.op_mode.temporal_position:
+            # the reference broadcasts the single EMA frame against the [T,1,H,dh] embedding and then fails on the
+            # [B,1] mask (src/models.py:326-329, 138): the combination only works with temporal_position = 0
+            raise NotImplementedError("op_mode.ema_frame needs op_mode.temporal_position = 0")
         if accelerator is not None and hasattr(accelerator, "main_process_first"):
             with accelerator.main_process_first():
                 self.encoder = disable_gradients(clip.load(config.architecture, device="cpu")[0].visual.float())
@@ -494,6 +565,10 @@ class Detector(nn.Module):
                 if config.adapter.frozen:
                     self.adapter = disable_gradients(self.adapter)
         self.transform = self._transform(self.encoder.input_resolution)
+        if "patch_mask" in self.train_mode and self.train_mode.patch_mask.type == "guide":
+            import pickle
+            with open(self.train_mode.patch_mask.path, "rb") as f:  # reference :493-495
+                self.guide_map = pickle.load(f)
 
     # --------------------------------------------------------------------------------------------- predict
     def predict(self, x, m, with_video_features=False, with_adapt_features=False, train=False):
@@ -523,6 +598,8 @@ class Detector(nn.Module):
         if self.adapter is not None:
             self.adapter.apply_packed(qkv, self.layer_indices, b * t, self.encoder.tokens_per_frame)  # :546-547
         kvs = self.taps_from_qkv(qkv, b, t)
+        if train and "patch_mask" in self.train_mode:
+            kvs = self._mask_patches(kvs)
         if (torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters())) or \
                 (self.decoder.training and self.decoder.dropout > 0):
             # training step (or any caller that wants decoder gradients, or active dropout): differentiable decoder
@@ -536,8 +613,38 @@ class Detector(nn.Module):
             features["adapt"] = [{n: kv[n].float() for n in ("k", "v")} for kv in kvs]
         return task_logits, features
 
+    def _mask_patches(self, kvs):
+        """train_mode.patch_mask (reference :511-544): keep a random subset of the patch positions, drawn with numpy's
+        global RNG exactly like the reference ("batch": one draw shared by all layers, "sample": one per layer,
+        "guide": one per layer weighted by the guide map). The gathered K/V are compact bf16 tensors that the native
+        decoder attention streams through their own strides."""
+        import numpy as np
+        cfg = self.train_mode.patch_mask
+        num_patch = kvs[0]["k"].shape[2]
+        num_select = int(num_patch * cfg.ratio)
+        patch_indices = None
+        out = []
+        for i, kv in enumerate(kvs):
+            if cfg.type == "batch":
+                if patch_indices is None:
+                    patch_indices = np.random.choice(range(num_patch), num_select, replace=False)
+            elif cfg.type == "sample":
+                patch_indices = np.random.choice(range(num_patch), num_select, replace=False)
+            elif cfg.type == "guide":
+                patch_indices = np.random.choice(range(num_patch), num_select, replace=False,
+                                                 p=self.guide_map["v"][self.layer_indices[i]].flatten())
+            else:
+                raise NotImplementedError()
+            idx = torch.as_tensor(np.asarray(patch_indices), dtype=torch.long, device=kv["k"].device)
+            out.append({n: kv[n].index_select(2, idx) for n in kv})
+        return out
+
     def forward(self, x, y, m, comp=None, speed=None, train=False, single_task=None, *args, **kargs):
         """Eval: ``(task_losses, task_logits)``; train adds ``other_losses`` (reference :568-596, 738)."""
+        if "ema_frame" in self.op_mode and self.op_mode.ema_frame:
+            # exponential moving average over the frames -> one frame per clip (reference :572-578)
+            x = _native.ema_frames(x, float(self.op_mode.ema_frame))
+            m = m[:, 0].unsqueeze(1)
         task_logits, features = self.predict(x, m, with_video_features=True, train=train)
         task_losses = [
             loss_fn(logits, labels) if single_task is None or i == single_task else 0

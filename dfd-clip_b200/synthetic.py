@@ -110,7 +110,8 @@ def layer_indices(arch, decode_mode="stride", decode_stride=2, decode_indices=()
     return list(decode_indices)
 
 
-def decoder_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, visual=None):
+def decoder_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, visual=None, aug_query=False,
+                       global_prediction=False, temporal_position=True):
     """fp32 state dict of the temporal decoder (keys as in ``Decoder.state_dict()``), initialised the way the
     reference does it: ln_1 / ln_2 / mlp of block i copied from encoder layer taps[i] (src/models.py:178-229),
     everything else random."""
@@ -121,9 +122,18 @@ def decoder_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, visua
     scale = w ** -0.5
     sd = OrderedDict()
     sd["class_embedding"] = _randn(seed, "dec.class_embedding", (w,), scale)
-    sd["positional_embedding"] = _randn(seed, "dec.positional_embedding", (num_frames, 1, heads, w // heads), scale)
+    if temporal_position:
+        sd["positional_embedding"] = _randn(seed, "dec.positional_embedding", (num_frames, 1, heads, w // heads), scale)
     for i, o in enumerate(out_dims):
-        sd["proj%dx%d" % (i, o)] = _randn(seed, "dec.proj%dx%d" % (i, o), (w, o), scale)
+        if global_prediction:  # op_mode.global_prediction: one projection per tapped layer (src/models.py:309-313)
+            for layer in taps:
+                name = "proj%dx%d_L%d" % (i, o, layer)
+                sd[name] = _randn(seed, "dec." + name, (w, o), scale)
+        else:
+            sd["proj%dx%d" % (i, o)] = _randn(seed, "dec.proj%dx%d" % (i, o), (w, o), scale)
+    if aug_query:  # op_mode.aug_query (src/models.py:250-255); zero-initialised there, random here
+        for i in range(len(taps) - 1):
+            sd["transformer.augment_query_%d" % i] = _randn(seed, "dec.augment_query_%d" % i, (w,), 0.5)
     for ln in ("ln_pre", "ln_post"):
         sd[ln + ".weight"] = _randn(seed, "dec." + ln + ".weight", (w,), 0.1, 1.0)
         sd[ln + ".bias"] = _randn(seed, "dec." + ln + ".bias", (w,), 0.1)
@@ -181,13 +191,14 @@ def adapter_state_dict(arch, n_taps, struct_type, inner=256, seed=0):
     return sd
 
 
-def detector_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, adapter=None, adapter_inner=256):
+def detector_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, adapter=None, adapter_inner=256,
+                        **decoder_options):
     """Full ``Detector.state_dict()`` (encoder.* + decoder.* [+ adapter.*]), the on-disk format of ``*_weights.pt``
     (written at main.py:119-129, loaded strictly at inference.py:99). ``adapter`` = an
     ``adapter.struct.type`` string adds the CompInvAdapter parameters."""
     visual = visual_state_dict(arch, seed)
     sd = OrderedDict(("encoder." + k, v) for k, v in visual.items())
-    for k, v in decoder_state_dict(arch, num_frames, out_dims, taps, seed, visual).items():
+    for k, v in decoder_state_dict(arch, num_frames, out_dims, taps, seed, visual, **decoder_options).items():
         sd["decoder." + k] = v
     if adapter is not None:
         n_taps = len(layer_indices(arch) if taps is None else list(taps))

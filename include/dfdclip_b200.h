@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DFD_ABI_VERSION 1
+#define DFD_ABI_VERSION 2
 
 enum {
   DFD_OK = 0,
@@ -140,6 +140,8 @@ int dfd_encoder_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pack
  * Decoder: Decoder.forward / Transformer.forward / MultiheadAttention.forward (src/models.py:323-361,
  * 259-269, 136-146) in fp32, streaming the tapped bf16 K/V once per block.
  * ---------------------------------------------------------------------------------------------------- */
+enum { DFD_ATTN_FRAME = 1, DFD_ATTN_TEMPORAL = 2 };
+
 typedef struct {
   const float* class_embedding;      /* [D] */
   const float* positional_embedding; /* [T,1,H,64] or NULL (op_mode.temporal_position == 0) */
@@ -160,6 +162,12 @@ typedef struct {
   const float* const* c_fc_bias;
   const float* const* c_proj_weight;
   const float* const* c_proj_bias;
+  /* op_mode.aug_query (src/models.py:250-255, 265-267): HOST array of n_blocks - 1 device pointers to fp32 [D]
+   * vectors added to the query after every block but the last, or NULL. */
+  const float* const* augment_query;
+  /* op_mode.attn_mode (src/models.py:107-115): 0 = softmax over all T*P keys (default), else a combination of
+   * DFD_ATTN_FRAME (softmax over the patches of each frame) and DFD_ATTN_TEMPORAL (over the frames of each patch). */
+  int attn_mode;
 } dfd_decoder_weights;
 
 /* K/V of tapped layer i: element (b,t,p,h,c) lives at k[i] + b*stride_b + t*stride_t + p*stride_p + h*64 + c
@@ -170,7 +178,8 @@ typedef struct {
   int64_t stride_b, stride_t, stride_p;
 } dfd_kv_taps;
 
-size_t dfd_decoder_workspace_bytes(int B, int T, int D, int n_blocks);
+/* P and attn_mode size the score buffers of the non-default attention modes (0 for the default mode). */
+size_t dfd_decoder_workspace_bytes(int B, int T, int P, int D, int n_blocks, int attn_mode);
 
 /* mask: uint8 [B,T] (1 = frame present; src/models.py:324). block_out: fp32 [B, n_blocks, D] (x after every
  * block, the torch.cat of models.py:269). video_feature: fp32 [B, D] = ln_post(block_out[:, -1]) (:340-343). */
@@ -183,12 +192,26 @@ int dfd_decoder_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_deco
 int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, int B, int D, int O, float scale,
                        float* logits, void* stream);
 
+/* op_mode.ema_frame (src/models.py:572-578): out[b] = EMA over the T frames of clip b, _x = _x*ratio + x[:, i]*(1-ratio)
+ * starting from zero, evaluated in that order in fp32. x fp32 [B, T, frame_elems] -> out fp32 [B, frame_elems];
+ * frame_elems % 4 == 0. */
+int dfd_ema_frames(dfd_ctx* ctx, const float* x, float* out, int B, int T, int64_t frame_elems, float ratio,
+                   void* stream);
+
 /* One decoder attention call on its own (models.py:136-146 without in/out projections), for unit tests:
  * qs fp32 [B, H, 128] = per head [smax query(64) | coda query(64)]; mix fp32 [B, H*64].
  * workspace: at least 2*B*T*H*130*4 bytes (partial records of the streaming kernel). */
 int dfd_decoder_attention(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                           int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
                           int T, int P, int H, float* mix, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dfd_decoder_attention for op_mode.attn_mode != 0 (DFD_ATTN_FRAME | DFD_ATTN_TEMPORAL): scores, per-group
+ * normalisation and the weighted sum of V as three passes. An all-masked softmax group yields NaN like the reference. */
+size_t dfd_decoder_attention_modes_workspace_bytes(int B, int T, int P, int H);
+int dfd_decoder_attention_modes(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
+                                int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask, int B,
+                                int T, int P, int H, int attn_mode, float* mix, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * CompInvAdapter on the tapped K/V (src/models.py:783-940; called from Detector.predict :546-547): a bottleneck

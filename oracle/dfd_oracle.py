@@ -75,15 +75,26 @@ def encoder_forward(sd, x, prefix="encoder.", with_out=False, with_q=False, num_
     return kvs
 
 
-def decoder_attention(qs, k, v, m):
+def decoder_attention(qs, k, v, m, attn_mode=(), num_frames=None):
     """MultiheadAttention.forward of the decoder without its projections (src/models.py:138-144) with the two
-    activations smax (:99-106, default attn_mode) and coda (:117-125).
+    activations smax (:99-115; ``attn_mode`` = () default, or a subset of {"frame", "temporal"}) and coda (:117-125).
     qs: [B,1,H,2*dh] per head [smax query | coda query]; k, v: [B,S,H,dh]; m: bool [B,S]. Returns [B,1,H,dh]."""
     dh = k.shape[-1]
     q0, q1 = qs.split(dh, dim=-1)                       # :137 view(B,1,H,-1).split(dh,-1)
     mm = m.unsqueeze(1).unsqueeze(-1)                   # :138
     norm = dh ** 0.5
-    smax = torch.einsum("nqhc,nkhc->nqkh", q0 / norm, k).masked_fill(~mm, float("-inf")).softmax(dim=-2)
+    smax = torch.einsum("nqhc,nkhc->nqkh", q0 / norm, k).masked_fill(~mm, float("-inf"))
+    if len(attn_mode) == 0:
+        smax = smax.softmax(dim=-2)                     # :105-106
+    else:                                               # :107-115
+        n, q, s, h = smax.shape
+        aff = smax.view(n, q, num_frames, -1, h)
+        parts = []
+        if "frame" in attn_mode:
+            parts.append(aff.softmax(dim=-2))
+        if "temporal" in attn_mode:
+            parts.append(aff.softmax(dim=-3))
+        smax = sum(parts).view(n, q, s, h)
     coda_aff = torch.einsum("nqhc,nkhc->nqkh", q1 / norm, k).tanh()
     gate = -(q1 - k).abs().sum(-1).unsqueeze(1) / norm
     gate = 2 * gate.sigmoid().masked_fill(~mm, 0.0)
@@ -91,10 +102,13 @@ def decoder_attention(qs, k, v, m):
     return torch.einsum("nqlh,nlhc->nqhc", aff, v)      # :144
 
 
-def decoder_forward(sd, kvs, m, out_dims, prefix="decoder."):
-    """Decoder.forward (src/models.py:323-361, default op_mode) + Transformer.forward (:259-269) +
-    ResidualAttentionBlock.forward (:173-176). kvs: list of {k, v: [B,T,P,H,dh]} (CLS already dropped);
-    m: bool [B,T]. Returns (raw task logits, video feature [B,D], block outputs [B, n_blocks, D])."""
+def decoder_forward(sd, kvs, m, out_dims, prefix="decoder.", layer_indices=None, attn_mode=()):
+    """Decoder.forward (src/models.py:323-361) + Transformer.forward (:259-269) + ResidualAttentionBlock.forward
+    (:173-176). kvs: list of {k, v: [B,T,P,H,dh]} (CLS already dropped); m: bool [B,T].
+    op_mode is inferred from the state dict like the constructor creates parameters: ``augment_query_{i}`` present =
+    aug_query (:250-255, 265-267); ``proj{i}x{o}_L{l}`` present = global_prediction (:309-313, 345-357; needs
+    ``layer_indices``); no ``positional_embedding`` = temporal_position off.
+    Returns (raw task logits, video feature [B,D] ([B,n_blocks,D] with global_prediction), block outputs)."""
     b, t, p, heads, dh = kvs[0]["k"].shape
     width = heads * dh
     mm = m.repeat_interleave(p, dim=-1)                                  # :324
@@ -112,12 +126,21 @@ def decoder_forward(sd, kvs, m, out_dims, prefix="decoder."):
         bp = "%stransformer.resblocks.%d." % (prefix, i)
         y = _ln(x, sd, bp + "ln_1")
         qs = F.linear(y, sd[bp + "attn.in_proj.weight"], sd[bp + "attn.in_proj.bias"]).view(b, 1, heads, -1)  # :137
-        mix = decoder_attention(qs, k, v, mm)
+        mix = decoder_attention(qs, k, v, mm, attn_mode, t)
         x = x + F.linear(mix.flatten(-2), sd[bp + "attn.out_proj.weight"], sd[bp + "attn.out_proj.bias"])   # :146, :174
         g = F.linear(_ln(x, sd, bp + "ln_2"), sd[bp + "mlp.c_fc.weight"], sd[bp + "mlp.c_fc.bias"])
         x = x + F.linear(_quick_gelu(g), sd[bp + "mlp.c_proj.weight"], sd[bp + "mlp.c_proj.bias"])          # :175
         outs.append(x)
+        aug = sd.get("%stransformer.augment_query_%d" % (prefix, i))
+        if aug is not None and i != len(flat) - 1:                       # :265-267
+            x = x + aug
     blocks = torch.cat(outs, dim=1)                                      # :269
+    if any(key.startswith(prefix + "proj0x") and "_L" in key for key in sd):   # global_prediction
+        feat = _ln(blocks, sd, prefix + "ln_post")                       # :342 on every block output
+        n = len(layer_indices)
+        logits = [sum((feat[:, j] @ sd["%sproj%dx%d_L%d" % (prefix, i, o, l)]) * (j + 1) / ((1 + n) * n / 2)
+                      for j, l in enumerate(layer_indices)) for i, o in enumerate(out_dims)]   # :345-357
+        return logits, feat, blocks
     feat = _ln(blocks[:, -1], sd, prefix + "ln_post")                    # :340-343
     logits = [feat @ sd["%sproj%dx%d" % (prefix, i, o)] for i, o in enumerate(out_dims)]  # :359
     return logits, feat, blocks
@@ -165,16 +188,29 @@ def normalise_logits(task_logits):
     return [5 * l / (torch.norm(l, dim=-1, keepdim=True) + 1e-10) for l in task_logits]
 
 
-def detector_predict(sd, x, m, layer_indices, out_dims, return_taps=False, adapter=None):
-    """Detector.predict (src/models.py:498-566, no patch mask; ``adapter`` = adapter.struct.type or None).
+def ema_frames(x, m, ratio):
+    """op_mode.ema_frame in Detector.forward (src/models.py:572-578)."""
+    b, t, c, h, w = x.shape
+    _x = torch.zeros((b, 1, c, h, w))
+    for i in range(t):
+        _x = _x * ratio + x[:, i].unsqueeze(1) * (1 - ratio)
+    return _x, m[:, 0].unsqueeze(1)
+
+
+def detector_predict(sd, x, m, layer_indices, out_dims, return_taps=False, adapter=None, attn_mode=(),
+                     patch_indices=None):
+    """Detector.predict (src/models.py:498-566; ``adapter`` = adapter.struct.type or None; ``patch_indices`` = the
+    per-layer index arrays train_mode.patch_mask drew, :511-544).
     x: fp32 [B,T,3,R,R]; m: bool [B,T]. Returns (normalised task logits, video feature[, taps])."""
     b, t = x.shape[:2]
     run = max(layer_indices) + 1
     enc = encoder_forward(sd, x.flatten(0, 1), num_layers=run)                                   # :503
     kvs = [{n: enc[i][n][:, 1:].unflatten(0, (b, t)) for n in ("k", "v")} for i in layer_indices]  # :505-509
+    if patch_indices is not None:
+        kvs = [{n: kv[n][:, :, idx] for n in kv} for kv, idx in zip(kvs, patch_indices)]         # :543-544
     if adapter is not None:
         kvs = adapter_forward(sd, kvs, adapter)                                                  # :546-547
-    logits, feat, _ = decoder_forward(sd, kvs, m, out_dims)                                      # :549
+    logits, feat, _ = decoder_forward(sd, kvs, m, out_dims, layer_indices=layer_indices, attn_mode=attn_mode)  # :549
     logits = normalise_logits(logits)
     if return_taps:
         return logits, feat, kvs

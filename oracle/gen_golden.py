@@ -45,6 +45,18 @@ CASES = {
     "tiny_ad_linear": ("tiny-256x4", 4, 3, True, "linear"),
     "vitb16_ad_nln": ("ViT-B/16", 8, 2, False, "768-x-768-nln"),
     "vitb16_ad_z0": ("ViT-B/16", 8, 2, False, "768-x-768-z0"),
+    # non-default decoder modes (src/models.py:107-115, 250-267, 345-357, 511-544, 572-578)
+    "tiny_aug_query": ("tiny-256x4", 4, 3, True, None, {"aug_query": 1}),
+    "tiny_global_pred": ("tiny-256x4", 4, 3, True, None, {"global_prediction": 1}),
+    "small_gp_aq": ("small-512x6", 3, 2, False, None, {"global_prediction": 1, "aug_query": 1}),
+    "tiny_ema": ("tiny-256x4", 4, 3, True, None, {"ema_frame": 0.3, "temporal_position": 0}),
+    "tiny_no_tpos": ("tiny-256x4", 4, 3, True, None, {"temporal_position": 0}),
+    "tiny_attn_frame": ("tiny-256x4", 4, 3, True, None, {"attn_mode": "frame"}),
+    "tiny_attn_tf": ("tiny-256x4", 4, 3, True, None, {"attn_mode": "temporal+frame"}),
+    "small_attn_temporal": ("small-512x6", 3, 2, False, None, {"attn_mode": "temporal"}),
+    "small_pm_batch": ("small-512x6", 3, 2, False, None, None, {"type": "batch", "ratio": 0.5}),
+    "small_pm_sample": ("small-512x6", 3, 2, False, None, None, {"type": "sample", "ratio": 0.5}),
+    "tiny_pm_adapter": ("tiny-256x4", 4, 3, True, "768-x-768-z0", None, {"type": "batch", "ratio": 0.5}),
 }
 N_SAMPLES = 4096
 
@@ -101,7 +113,7 @@ def sample_indices(numel, seed):
     return torch.randint(0, numel, (min(N_SAMPLES, numel),), generator=g)
 
 
-def run_case(name, arch, num_frames, batch, full, adapter=None):
+def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, patch_mask=None):
     from src.models import Detector  # the reference's own class
 
     dims = synthetic.vit_dims(arch)
@@ -113,8 +125,12 @@ def run_case(name, arch, num_frames, batch, full, adapter=None):
     cfg.architecture = ckpt
     cfg.out_dim = [2]
     cfg.losses = ["auc_roc"]
+    from yacs.config import CfgNode
+    for key, val in (op_mode or {}).items():
+        cfg.op_mode[key] = val
+    if patch_mask is not None:
+        cfg.train_mode["patch_mask"] = CfgNode(dict(patch_mask))
     if adapter is not None:
-        from yacs.config import CfgNode
         cfg.adapter.type = "normal"
         cfg.adapter.frozen = 0
         cfg.adapter.struct = CfgNode({"type": adapter, "x": 256})
@@ -122,8 +138,11 @@ def run_case(name, arch, num_frames, batch, full, adapter=None):
     det = Detector(cfg, num_frames, FakeAccelerator())
     os.remove(ckpt)
 
+    op = dict(op_mode or {})
     sd = synthetic.detector_state_dict(arch, num_frames, out_dims=(2,), taps=det.layer_indices, seed=0,
-                                       adapter=adapter, adapter_inner=256)
+                                       adapter=adapter, adapter_inner=256, aug_query=bool(op.get("aug_query")),
+                                       global_prediction=bool(op.get("global_prediction")),
+                                       temporal_position=bool(op.get("temporal_position", 1)))
     # the encoder built by the reference's clip.load/build_model must equal the synthetic fp32 values exactly
     # (they are fp16-representable where build_model rounds)
     for k, v in det.encoder.state_dict().items():
@@ -134,18 +153,45 @@ def run_case(name, arch, num_frames, batch, full, adapter=None):
 
     x, m = synthetic.make_clips(batch, num_frames, dims["image_size"], seed=7)
     labels = torch.arange(batch) % 2
+    extra = {}
     with torch.no_grad():
         taps = det.encoder(x.flatten(0, 1), with_out=True, with_q=True)
-        logits, feats = det.predict(x, m, with_video_features=True, with_adapt_features=adapter is not None)
-        losses, logits2 = det(x, [labels], m, single_task=0)
-    assert torch.equal(logits[0], logits2[0])
+        if patch_mask is not None:
+            # train_mode.patch_mask only acts with train=True (:511); the module stays in eval mode (dropout is 0)
+            np.random.seed(1234)
+            logits, feats = det.predict(x, m, with_video_features=True, with_adapt_features=adapter is not None,
+                                        train=True)
+            np.random.seed(1234)
+            losses, logits2, _ = det(x, [labels], m, single_task=0, train=True)
+            np.random.seed(1234)   # the index draws, for the oracle (same numpy calls as :511-541)
+            num_patch = (dims["image_size"] // dims["patch_size"]) ** 2
+            num_select = int(num_patch * patch_mask["ratio"])
+            drawn, idx = [], None
+            for _ in det.layer_indices:
+                if patch_mask["type"] == "sample" or idx is None:
+                    idx = np.random.choice(range(num_patch), num_select, replace=False)
+                drawn.append(idx)
+            extra["patch_indices"] = np.stack(drawn)
+            extra["patch_mask_type"] = np.array(patch_mask["type"])
+            extra["patch_mask_ratio"] = np.array(patch_mask["ratio"])
+        elif op.get("ema_frame"):
+            # ema_frame acts in Detector.forward, not in predict (:572-578)
+            losses, logits = det(x, [labels], m, single_task=0)
+            logits2, feats = logits, {"video": np.zeros((0,), dtype=np.float32)}
+        else:
+            logits, feats = det.predict(x, m, with_video_features=True, with_adapt_features=adapter is not None)
+            losses, logits2 = det(x, [labels], m, single_task=0)
+    assert torch.allclose(logits[0], logits2[0], rtol=0, atol=0, equal_nan=True)
 
     out = {
         "arch": np.array(arch), "num_frames": np.array(num_frames), "batch": np.array(batch),
         "layer_indices": np.array(det.layer_indices), "mask": m.numpy(), "labels": labels.numpy(),
-        "logits": logits[0].numpy(), "video_feature": feats["video"].numpy(), "losses": losses[0].numpy(),
+        "logits": logits[0].numpy(), "video_feature": np.asarray(feats["video"]), "losses": losses[0].numpy(),
         "pred_labels": logits[0].argmax(-1).numpy(),
     }
+    out.update(extra)
+    if op_mode:
+        out["op_mode"] = np.array(repr(sorted(op.items())))
     if adapter is not None:
         out["adapter"] = np.array(adapter)
         # adapted taps as the decoder received them: predict's kvs after the adapter AND after Decoder.forward's
@@ -163,8 +209,8 @@ def run_case(name, arch, num_frames, batch, full, adapter=None):
                     out["idx_adapt_%s_%d" % (key, i)] = idx.numpy()
                     out["val_adapt_%s_%d" % (key, i)] = t.flatten()[idx].detach().numpy()
     for i, a in enumerate(taps):
-        if adapter is not None:
-            break  # the raw taps are pinned by the adapter-less cases
+        if adapter is not None or op_mode or patch_mask:
+            break  # the raw taps are pinned by the default-mode cases
         for key in ("q", "k", "v", "out"):
             t = a[key].contiguous().float()
             out["norm_%s_%d" % (key, i)] = np.array(t.norm().item(), dtype=np.float64)

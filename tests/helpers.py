@@ -32,13 +32,22 @@ def load_golden(name):
     return out
 
 
+def golden_op_mode(g):
+    """op_mode overrides the golden case was generated with (empty for the default configuration)."""
+    import ast
+    return dict(ast.literal_eval(str(g["op_mode"]))) if "op_mode" in g else {}
+
+
 def golden_inputs(g):
     """The exact (state_dict, clips, mask) the golden generator fed the reference."""
     from dfdclip_b200 import synthetic
     dims = synthetic.vit_dims(g["arch"])
     adapter = str(g["adapter"]) if "adapter" in g else None
+    op = golden_op_mode(g)
     sd = synthetic.detector_state_dict(g["arch"], g["num_frames"], out_dims=(2,), taps=g["layer_indices"], seed=0,
-                                       adapter=adapter, adapter_inner=256)
+                                       adapter=adapter, adapter_inner=256, aug_query=bool(op.get("aug_query")),
+                                       global_prediction=bool(op.get("global_prediction")),
+                                       temporal_position=bool(op.get("temporal_position", 1)))
     x, m = synthetic.make_clips(g["batch"], g["num_frames"], dims["image_size"], seed=7)
     assert np.array_equal(m.numpy(), g["mask"])
     return sd, x, m

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "libdfdclip_b200.so does not export " + name
     assert declared == set(nat.EXPORTS), (declared ^ set(nat.EXPORTS))
-    assert lib.dfd_version() == 1
+    assert lib.dfd_version() == 2
 
 
 def test_native_refuses_without_gpu():
@@ -47,7 +47,8 @@ def test_workspace_size_queries_do_not_need_a_gpu():
     assert ws >= 512 * 197 * 768 * (4 + 2 + 2 + 8 + 6)
     bad = nat.VitDims(224, 16, 700, 12, 12)
     assert lib.dfd_encoder_packed_bytes(ctypes.byref(bad)) == 0
-    assert lib.dfd_decoder_workspace_bytes(64, 8, 768, 6) > 0
+    assert lib.dfd_decoder_workspace_bytes(64, 8, 196, 768, 6, 0) > 0
+    assert lib.dfd_decoder_workspace_bytes(64, 8, 196, 768, 6, 3) > lib.dfd_decoder_workspace_bytes(64, 8, 196, 768, 6, 0)
 
 
 # ------------------------------------------------------------------------------- loader / Detector surface
@@ -109,8 +110,8 @@ def test_index_decode_mode_and_unsupported_knobs():
     det, _ = _detector(decode_mode="index", decode_indices=[1, 3])
     assert det.layer_indices == [1, 3]
     from dfdclip_b200.models import Detector
-    for mutate in (lambda c: c.op_mode.__setitem__("attn_mode", "frame"),
-                   lambda c: c.op_mode.__setitem__("aug_query", 1),
+    for mutate in (lambda c: c.op_mode.__setitem__("attn_mode", "spatial"),
+                   lambda c: c.op_mode.__setitem__("ema_frame", 0.3),  # needs temporal_position = 0
                    lambda c: c.adapter.__setitem__("type", "lora"),
                    lambda c: (c.adapter.__setitem__("type", "normal"),
                               c.adapter.__setitem__("struct", CN({"type": "768-bn", "x": 256}))),

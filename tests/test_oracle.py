@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import cosine, golden_inputs, golden_tensor, load_golden, load_oracle
+from helpers import cosine, golden_inputs, golden_op_mode, golden_tensor, load_golden, load_oracle
 
 CASES = ["tiny", "small", "vitb16", "vitl14"]
 
@@ -55,6 +55,34 @@ def test_oracle_adapter_matches_reference_golden(oracle, case):
         for key in ("k", "v"):
             ref, got = golden_tensor(g, "adapt_" + key, i, kv[key])
             assert (got - ref).abs().max().item() <= 2e-4 * max(ref.abs().max().item(), 1.0), (case, i, key)
+
+
+MODE_CASES = ["tiny_aug_query", "tiny_global_pred", "small_gp_aq", "tiny_ema", "tiny_no_tpos", "tiny_attn_frame",
+              "tiny_attn_tf", "small_attn_temporal", "small_pm_batch", "small_pm_sample", "tiny_pm_adapter"]
+
+
+@pytest.mark.parametrize("case", MODE_CASES)
+def test_oracle_decoder_modes_match_reference_golden(oracle, case):
+    """Non-default op_mode / train_mode switches of the decoder (src/models.py:107-115, 250-267, 345-357, 511-544,
+    572-578) against the unmodified reference. attn_mode with "frame" gives NaN for clips with a padded frame in the
+    reference (softmax over an all -inf frame, :111): NaN positions must coincide."""
+    g = load_golden(case)
+    sd, x, m = golden_inputs(g)
+    op = golden_op_mode(g)
+    attn_mode = tuple(op["attn_mode"].split("+")) if "attn_mode" in op else ()
+    adapter = str(g["adapter"]) if "adapter" in g else None
+    with torch.no_grad():
+        if op.get("ema_frame"):
+            x, m = oracle.ema_frames(x, m, op["ema_frame"])
+        pi = [torch.from_numpy(i) for i in g["patch_indices"]] if "patch_indices" in g else None
+        logits, feat = oracle.detector_predict(sd, x, m, g["layer_indices"], (2,), adapter=adapter,
+                                               attn_mode=attn_mode, patch_indices=pi)
+    got, ref = logits[0].numpy(), g["logits"]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.nanmax(np.abs(got - ref)) < 1e-4
+    if g["video_feature"].size:
+        assert np.nanmax(np.abs(feat.numpy() - g["video_feature"])) < 2e-4
+        assert feat.numpy().shape == g["video_feature"].shape
 
 
 def test_z0_adapter_is_identity_at_init(oracle):
