@@ -49,10 +49,10 @@ def flops_per_clip(dims, frames, taps, executed=True):
     return per_frame * frames, gemm * frames
 
 
-def launches_per_predict(layers_run_full, n_taps, n_tasks):
+def launches_per_predict(layers_run_full, n_taps, n_tasks, adapter=False):
     enc = 4 + 7 * layers_run_full + 2
     dec = 2 + 9 * n_taps + 1 + n_tasks
-    return enc + dec
+    return enc + dec + (6 * n_taps if adapter else 0)  # adapter: down GEMM, norm/act kernel, up GEMM per k and v
 
 
 def load_peaks():
@@ -139,15 +139,23 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def build_detector(arch, frames, device):
+def build_detector(arch, frames, device, adapter=None, taps=None):
     from dfdclip_b200 import synthetic
+    from dfdclip_b200.config import CN
     from dfdclip_b200.models import Detector
     cfg = Detector.get_default_config()
     cfg.architecture = "synthetic:" + arch
     cfg.out_dim = [2]
     cfg.losses = ["auc_roc"]
+    if taps:
+        cfg.decode_mode = "index"
+        cfg.decode_indices = list(taps)
+    if adapter:
+        cfg.adapter.type = "normal"
+        cfg.adapter.frozen = 0
+        cfg.adapter.struct = CN({"type": adapter, "x": 256})
     det = Detector(cfg, frames, None)
-    sd = synthetic.detector_state_dict(arch, frames, out_dims=(2,), taps=det.layer_indices, seed=0)
+    sd = synthetic.detector_state_dict(arch, frames, out_dims=(2,), taps=det.layer_indices, seed=0, adapter=adapter)
     det.load_state_dict(sd, strict=True)
     return det.to(device).eval(), sd
 
@@ -222,7 +230,8 @@ def run_b200(args, rank, world, local_rank):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
     dims = synthetic.vit_dims(args.arch)
-    det, _ = build_detector(args.arch, args.frames, dev)
+    det, _ = build_detector(args.arch, args.frames, dev, adapter=args.adapter,
+                            taps=[int(t) for t in args.taps.split(",")] if args.taps else None)
     taps = det.layer_indices
     clips, frames, res = args.clips, args.frames, dims["image_size"]
 
@@ -338,13 +347,14 @@ def run_b200(args, rank, world, local_rank):
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "C2: %s encoder + DFD head eval, %d synthetic clips x %d frames x %d^2 per GPU per step" % (
-            args.arch, clips, frames, res), "arch": args.arch, "clips_per_gpu": clips, "frames": frames, "taps": taps,
+            args.arch, clips, frames, res) + (" + CompInvAdapter %s" % args.adapter if args.adapter else ""),
+            "arch": args.arch, "clips_per_gpu": clips, "frames": frames, "taps": taps, "adapter": args.adapter,
             "parallelism": "dp%d" % world, "l2": "inputs_exceed_l2 (%.0f MB of fp32 frames per step)" % (
                 x.numel() * 4 / 1e6), "flops_per_clip_executed": total_flops, "flops_per_clip_reference": ref_flops,
             "kernel_timing": "separate pass of %d steps with one CUDA event pair per launch" % kt_steps},
         "clocks": clocks.summary(),
         "e2e": e2e,
-        "gpu_launches": launches_per_predict(n_full, len(taps), 1) * args.steps,
+        "gpu_launches": launches_per_predict(n_full, len(taps), 1, bool(args.adapter)) * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
@@ -360,6 +370,10 @@ def main():
     ap.add_argument("--arch", default="ViT-B/16")
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--adapter", default=None, help="adapter.struct.type of a CompInvAdapter (x=256) on the taps, "
+                    "e.g. 768-x-768-nln as in the shipped configs; default: none (BASELINE config C2)")
+    ap.add_argument("--taps", default=None, help="comma-separated decode_indices (decode_mode=index), e.g. "
+                    "6,7,8,9,10,11 as in the shipped configs; default: stride-2 taps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
