@@ -285,7 +285,7 @@ def run_b200(args, rank, world, local_rank):
     value = world * clips * args.steps / (elapsed_ms * 1e-3)
 
     # ---- same metric end to end through the public API with HOST buffers (pinned H2D in, logits D2H out)
-    e2e = None
+    e2e = e2e_u8 = None
     if not args.no_e2e:
         from dfdclip_b200.inference import predict_from_host
         for _ in range(2):
@@ -305,6 +305,29 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"value": world * clips * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + m_host.numel(),
                "d2h_bytes_per_step": host_logits.numel() * host_logits.element_size()}
+        # same call on raw uint8 pixels (Detector.transform_uint8): float conversion + normalisation fused into the
+        # patch extraction kernel, 1 byte per pixel over PCIe. Reported next to `e2e`, which keeps the reference's
+        # fp32 clip format.
+        g8 = torch.Generator().manual_seed(70 + rank)
+        x8_host = torch.randint(0, 256, tuple(x_host.shape), generator=g8, dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            predict_from_host(det, x8_host, m_host)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            predict_from_host(det, x8_host, m_host)
+        torch.cuda.synchronize()
+        dt8 = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt8], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt8 = t.item()
+        e2e_u8 = {"value": world * clips * args.steps / dt8, "unit": UNIT,
+                  "h2d_bytes_per_step": x8_host.numel() + m_host.numel(),
+                  "d2h_bytes_per_step": host_logits.numel() * host_logits.element_size(),
+                  "input": "uint8 pixels, normalisation fused into patchify"}
 
     if rank != 0:
         return
@@ -354,6 +377,7 @@ def run_b200(args, rank, world, local_rank):
             "kernel_timing": "separate pass of %d steps with one CUDA event pair per launch" % kt_steps},
         "clocks": clocks.summary(),
         "e2e": e2e,
+        "e2e_u8": e2e_u8,
         "gpu_launches": launches_per_predict(n_full, len(taps), 1, bool(args.adapter)) * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,

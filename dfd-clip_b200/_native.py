@@ -27,6 +27,7 @@ EXPORTS = (
     "dfd_decoder_attention_workspace_bytes", "dfd_decoder_attention_train", "dfd_decoder_attention_backward",
     "dfd_adapter_workspace_bytes", "dfd_adapter_apply", "dfd_ema_frames",
     "dfd_decoder_attention_modes_workspace_bytes", "dfd_decoder_attention_modes",
+    "dfd_patchify_u8", "dfd_encoder_forward_u8",
 )
 
 
@@ -104,6 +105,11 @@ def load_library():
                                                  c_void_p, c_void_p]
         lib.dfd_encoder_forward.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p, c_int, c_int,
                                             c_int, _PP, _PP, c_void_p, c_size_t, c_void_p]
+        lib.dfd_patchify_u8.argtypes = [c_void_p, c_void_p, ctypes.POINTER(c_float), c_void_p, c_int, c_int, c_int,
+                                        c_int, c_void_p]
+        lib.dfd_encoder_forward_u8.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p,
+                                               ctypes.POINTER(c_float), c_int, c_int, c_int, _PP, _PP, c_void_p,
+                                               c_size_t, c_void_p]
         lib.dfd_decoder_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
         lib.dfd_decoder_workspace_bytes.restype = c_size_t
         lib.dfd_decoder_forward.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
@@ -226,16 +232,26 @@ def layernorm(x, gamma, beta, pos=None, out_dtype=torch.bfloat16, out=None):
     return out
 
 
-def patchify(frames, patch, kp=None):
-    """frames fp32 [F,3,R,R] -> bf16 [F*(P+1), Kp] patch matrix with zero cls rows."""
-    assert frames.dtype == torch.float32 and frames.is_contiguous() and frames.dim() == 4
+def mean_std_array(mean, std):
+    """HOST float[6] = {mean[3], std[3]} for the uint8 entry points."""
+    return (c_float * 6)(*[float(v) for v in mean], *[float(v) for v in std])
+
+
+def patchify(frames, patch, kp=None, mean=None, std=None):
+    """frames fp32 [F,3,R,R] (or uint8 with per-channel ``mean`` / ``std``: (x/255 - mean)/std is applied on the
+    fly) -> bf16 [F*(P+1), Kp] patch matrix with zero cls rows."""
+    assert frames.dtype in (torch.float32, torch.uint8) and frames.is_contiguous() and frames.dim() == 4
     f, _, r, _ = frames.shape
     k = 3 * patch * patch
     kp = kp or (k + 63) // 64 * 64
     g = r // patch
     out = torch.empty((f * (g * g + 1), kp), dtype=torch.bfloat16, device=frames.device)
-    check(load_library().dfd_patchify(ctx(frames.device), ptr(frames), ptr(out), f, r, patch, kp,
-                                      stream_ptr(frames.device)))
+    if frames.dtype == torch.uint8:
+        check(load_library().dfd_patchify_u8(ctx(frames.device), ptr(frames), mean_std_array(mean, std), ptr(out), f,
+                                             r, patch, kp, stream_ptr(frames.device)))
+    else:
+        check(load_library().dfd_patchify(ctx(frames.device), ptr(frames), ptr(out), f, r, patch, kp,
+                                          stream_ptr(frames.device)))
     return out
 
 

@@ -88,6 +88,10 @@ class VisionTransformer(nn.Module):
         self._packed = None
         self._packed_key = None
         self._workspace = None
+        # normalisation applied on the fly to uint8 frames: the constants of the reference's CLIP transform
+        # (src/models.py:762-768); Detector overrides them when its transform uses other values
+        self.input_mean = (0.48145466, 0.4578275, 0.40821073)
+        self.input_std = (0.26862954, 0.26130258, 0.27577711)
 
     # ---------------------------------------------------------------------------------------------- native
     @property
@@ -188,7 +192,10 @@ class VisionTransformer(nn.Module):
         lib = _native.load_library()
         dev = x.device
         x = x.detach()
-        if x.dtype != torch.float32 or not x.is_contiguous():
+        if x.dtype == torch.uint8:
+            # raw pixels: ConvertImageDtype(float32) + Normalize of the data loader are fused into the patchify kernel
+            x = x.contiguous()
+        elif x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         n = x.shape[0]
         seq, d = self.tokens_per_frame, self.width
@@ -220,12 +227,18 @@ class VisionTransformer(nn.Module):
         ws = self._get_workspace(ws_bytes, dev)
         qkv_arr = _native.ptr_array([qkv.get(l) for l in range(self.layers)])
         out_arr = _native.ptr_array([outs.get(l) for l in range(self.layers)]) if need_out else None
+        qkv_pp = ctypes.cast(qkv_arr, ctypes.POINTER(ctypes.c_void_p))
+        out_pp = ctypes.cast(out_arr, ctypes.POINTER(ctypes.c_void_p)) if need_out else None
         with torch.cuda.device(dev):
-            _native.check(lib.dfd_encoder_forward(
-                _native.ctx(dev), ctypes.byref(dims), _native.ptr(packed), _native.ptr(x), n, run_layers,
-                1 if qkv_only else 0, ctypes.cast(qkv_arr, ctypes.POINTER(ctypes.c_void_p)),
-                ctypes.cast(out_arr, ctypes.POINTER(ctypes.c_void_p)) if need_out else None,
-                _native.ptr(ws), ws_bytes, _native.stream_ptr(dev)))
+            if x.dtype == torch.uint8:
+                _native.check(lib.dfd_encoder_forward_u8(
+                    _native.ctx(dev), ctypes.byref(dims), _native.ptr(packed), _native.ptr(x),
+                    _native.mean_std_array(self.input_mean, self.input_std), n, run_layers, 1 if qkv_only else 0,
+                    qkv_pp, out_pp, _native.ptr(ws), ws_bytes, _native.stream_ptr(dev)))
+            else:
+                _native.check(lib.dfd_encoder_forward(
+                    _native.ctx(dev), ctypes.byref(dims), _native.ptr(packed), _native.ptr(x), n, run_layers,
+                    1 if qkv_only else 0, qkv_pp, out_pp, _native.ptr(ws), ws_bytes, _native.stream_ptr(dev)))
         return qkv, outs
 
     def forward(self, x, with_out=False, with_q=False):

@@ -18,7 +18,8 @@ int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int
               void* out, int64_t ldo, int M, int N, int K, int epilogue, cudaStream_t stream);
 int layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int pos_period, void* out_bf16,
               float* out_f32, int64_t rows, int D, cudaStream_t stream);
-int patchify(const float* frames, void* out, int n_frames, int R, int patch, int Kp, cudaStream_t stream);
+int patchify(const void* frames, void* out, int n_frames, int R, int patch, int Kp, cudaStream_t stream,
+             const float* mean_std);
 int mha_fwd(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
 int cast_pad_bf16(const float* src, void* dst, int64_t rows, int cols, int dst_ld, cudaStream_t stream);
 
@@ -152,9 +153,9 @@ int encoder_pack_weights(const dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd
   return 0;
 }
 
-int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const float* frames, int n_frames,
-                    int num_run_layers, int last_qkv_only, void* const* qkv_out, float* const* x_out, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream) {
+int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
+                    const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                    float* const* x_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VitShape s;
   DFD_TRY(vit_shape(dims, &s));
   DFD_CHECK_ARG(n_frames >= 0, "encoder_forward: negative frame count");
@@ -186,7 +187,7 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
     ScopedTimer _t(ctx, tag, stream);     \
     DFD_TRY(call);                        \
   } while (0)
-  DFD_TIMED(DFD_TAG_PATCHIFY, patchify(frames, patches, n_frames, s.R, s.p, s.Kp, stream));
+  DFD_TIMED(DFD_TAG_PATCHIFY, patchify(frames, patches, n_frames, s.R, s.p, s.Kp, stream, mean_std));
   DFD_TIMED(DFD_TAG_GEMM_PATCH,
             gemm_bf16(ctx, patches, s.Kp, pk + pl.conv_w, s.Kp, nullptr, x, D, M, D, s.Kp, DFD_EPI_STORE_F32, stream));
   DFD_TIMED(DFD_TAG_LAYERNORM,
@@ -246,8 +247,19 @@ int dfd_encoder_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pack
                         void* workspace, size_t workspace_bytes, void* stream) {
   dfd::clear_error();
   if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_encoder_forward: ctx is NULL");
-  return dfd::encoder_forward(ctx, dims, packed, frames, n_frames, num_run_layers, last_qkv_only, qkv_out, x_out,
-                              workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  return dfd::encoder_forward(ctx, dims, packed, frames, nullptr, n_frames, num_run_layers, last_qkv_only, qkv_out,
+                              x_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int dfd_encoder_forward_u8(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const uint8_t* frames,
+                           const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only,
+                           void* const* qkv_out, float* const* x_out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_encoder_forward_u8: ctx is NULL");
+  if (!mean_std) return dfd::fail(DFD_ERR_INVALID, "dfd_encoder_forward_u8: mean_std is NULL");
+  return dfd::encoder_forward(ctx, dims, packed, frames, mean_std, n_frames, num_run_layers, last_qkv_only, qkv_out,
+                              x_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

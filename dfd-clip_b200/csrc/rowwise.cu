@@ -102,8 +102,12 @@ int layernorm(const float* x, const float* gamma, const float* beta, const float
 // (src/clip/model.py:277-279). One thread moves 8 consecutive pixels of one image row (two float4 loads, one
 // 16-byte store); consecutive threads walk an image row, so loads are fully coalesced and every 32-byte store
 // sector is written whole. blockIdx.y = frame.
+// U8: frames are uint8 pixels; (x / 255 - mean[c]) / std[c] — ConvertImageDtype(float32) + Normalize of the
+// reference's CPU transform (src/models.py:762-768), same fp32 operation order — is applied on the fly.
+template <bool U8>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ out, int R, int patch, int G, int Kp) {
+patchify_kernel(const void* __restrict__ frames_raw, __nv_bfloat16* __restrict__ out, int R, int patch, int G, int Kp,
+                float3 mean, float3 stdv) {
   const int f = blockIdx.y;
   const int per_row = R / 8;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 3 * R * (R/8)
@@ -111,9 +115,25 @@ patchify_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ ou
   const int xs = (idx % per_row) * 8;
   const int y = (idx / per_row) % R;
   const int c = idx / (per_row * R);
-  const float* src = frames + ((static_cast<int64_t>(f) * 3 + c) * R + y) * R + xs;
-  const float4 a = *reinterpret_cast<const float4*>(src);
-  const float4 b = *reinterpret_cast<const float4*>(src + 4);
+  const int64_t off = ((static_cast<int64_t>(f) * 3 + c) * R + y) * R + xs;
+  float vals[8];
+  if constexpr (U8) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(frames_raw) + off);
+    const float mu = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
+    const float sd = c == 0 ? stdv.x : (c == 1 ? stdv.y : stdv.z);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t word = e < 4 ? raw.x : raw.y;
+      const float px = static_cast<float>((word >> (8 * (e & 3))) & 0xffu);
+      vals[e] = __fdiv_rn(__fsub_rn(__fdiv_rn(px, 255.0f), mu), sd);
+    }
+  } else {
+    const float* src = static_cast<const float*>(frames_raw) + off;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    vals[0] = a.x; vals[1] = a.y; vals[2] = a.z; vals[3] = a.w;
+    vals[4] = b.x; vals[5] = b.y; vals[6] = b.z; vals[7] = b.w;
+  }
   const int py = y / patch, i = y % patch;
   const int P = G * G;
   // 8 consecutive pixels may straddle two patches when patch % 8 != 0 (e.g. patch 14): split per element then.
@@ -121,10 +141,10 @@ patchify_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ ou
     const int px = xs / patch, j = xs % patch;
     const int64_t row = static_cast<int64_t>(f) * (P + 1) + 1 + py * G + px;
     const int col = (c * patch + i) * patch + j;
-    uint4 pk = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    uint4 pk = make_uint4(pack_bf16(vals[0], vals[1]), pack_bf16(vals[2], vals[3]), pack_bf16(vals[4], vals[5]),
+                          pack_bf16(vals[6], vals[7]));
     *reinterpret_cast<uint4*>(out + row * Kp + col) = pk;
   } else {
-    const float vals[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int x = xs + e;
@@ -154,7 +174,8 @@ __global__ void patchify_pad_kernel(__nv_bfloat16* __restrict__ out, int n_frame
   }
 }
 
-int patchify(const float* frames, void* out, int n_frames, int R, int patch, int Kp, cudaStream_t stream) {
+int patchify(const void* frames, void* out, int n_frames, int R, int patch, int Kp, cudaStream_t stream,
+             const float* mean_std /* NULL: fp32 frames; else uint8 frames with {mean[3], std[3]} */) {
   DFD_CHECK_ARG(frames && out, "patchify: null pointer");
   DFD_CHECK_ARG(n_frames >= 0 && R > 0 && patch > 0, "patchify: bad shape");
   DFD_CHECK_ARG(R % 8 == 0, "patchify: image size %d must be a multiple of 8", R);
@@ -173,7 +194,16 @@ int patchify(const float* frames, void* out, int n_frames, int R, int patch, int
   }
   patchify_pad_kernel<<<296, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(out), n_frames, G * G, K, Kp);
   DFD_CUDA_OK(cudaGetLastError());
-  patchify_kernel<<<grid, 256, 0, stream>>>(frames, static_cast<__nv_bfloat16*>(out), R, patch, G, Kp);
+  if (mean_std) {
+    DFD_CHECK_ARG(mean_std[3] != 0.f && mean_std[4] != 0.f && mean_std[5] != 0.f, "patchify: zero std");
+    DFD_CHECK_ARG(reinterpret_cast<uintptr_t>(frames) % 8 == 0, "patchify: uint8 frames must be 8-byte aligned");
+    patchify_kernel<true><<<grid, 256, 0, stream>>>(frames, static_cast<__nv_bfloat16*>(out), R, patch, G, Kp,
+                                                    make_float3(mean_std[0], mean_std[1], mean_std[2]),
+                                                    make_float3(mean_std[3], mean_std[4], mean_std[5]));
+  } else {
+    patchify_kernel<false><<<grid, 256, 0, stream>>>(frames, static_cast<__nv_bfloat16*>(out), R, patch, G, Kp,
+                                                     make_float3(0, 0, 0), make_float3(1, 1, 1));
+  }
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -211,5 +241,13 @@ extern "C" int dfd_patchify(dfd_ctx* ctx, const float* frames, void* out_bf16, i
                             void* stream) {
   dfd::clear_error();
   if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_patchify: ctx is NULL");
-  return dfd::patchify(frames, out_bf16, n_frames, R, patch, Kp, static_cast<cudaStream_t>(stream));
+  return dfd::patchify(frames, out_bf16, n_frames, R, patch, Kp, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+extern "C" int dfd_patchify_u8(dfd_ctx* ctx, const uint8_t* frames, const float* mean_std, void* out_bf16,
+                               int n_frames, int R, int patch, int Kp, void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_patchify_u8: ctx is NULL");
+  if (!mean_std) return dfd::fail(DFD_ERR_INVALID, "dfd_patchify_u8: mean_std is NULL");
+  return dfd::patchify(frames, out_bf16, n_frames, R, patch, Kp, static_cast<cudaStream_t>(stream), mean_std);
 }

@@ -49,8 +49,9 @@ class HostClipPipeline:
 
     def _buffers(self, x_host, rows):
         shape = (rows,) + tuple(x_host.shape[1:])
-        if self._bufs is None or self._bufs[0].shape[1:] != shape[1:] or self._bufs[0].shape[0] < rows:
-            self._bufs = [torch.empty(shape, dtype=torch.float32, device=self.dev) for _ in range(2)]
+        if self._bufs is None or self._bufs[0].shape[1:] != shape[1:] or self._bufs[0].shape[0] < rows \
+                or self._bufs[0].dtype != x_host.dtype:
+            self._bufs = [torch.empty(shape, dtype=x_host.dtype, device=self.dev) for _ in range(2)]  # fp32 or uint8
         return self._bufs
 
     def _tap_buffers(self, n_frames):
@@ -90,7 +91,7 @@ class HostClipPipeline:
         out_host.copy_(logits[0], non_blocking=True)
 
     def __call__(self, x_host, m_host, out_host=None):
-        """x_host fp32 [B,T,3,R,R], m_host bool [B,T] (pinned for real overlap). Returns logits of task 0 on the host
+        """x_host fp32 (normalised) or uint8 (raw pixels) [B,T,3,R,R], m_host bool [B,T] (pinned for real overlap). Returns logits of task 0 on the host
         (fp32 [B, out_dim], pinned); the call returns after the last D2H copy has completed."""
         n = x_host.shape[0]
         out_dim = self.det.out_dim[0]

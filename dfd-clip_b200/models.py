@@ -565,6 +565,7 @@ class Detector(nn.Module):
                 if config.adapter.frozen:
                     self.adapter = disable_gradients(self.adapter)
         self.transform = self._transform(self.encoder.input_resolution)
+        self.encoder.input_mean, self.encoder.input_std = self._MEAN, self._STD
         if "patch_mask" in self.train_mode and self.train_mode.patch_mask.type == "guide":
             import pickle
             with open(self.train_mode.patch_mask.path, "rb") as f:  # reference :493-495
@@ -643,6 +644,8 @@ class Detector(nn.Module):
         """Eval: ``(task_losses, task_logits)``; train adds ``other_losses`` (reference :568-596, 738)."""
         if "ema_frame" in self.op_mode and self.op_mode.ema_frame:
             # exponential moving average over the frames -> one frame per clip (reference :572-578)
+            if x.dtype == torch.uint8:
+                raise NotImplementedError("op_mode.ema_frame averages normalised float frames: pass fp32 clips")
             x = _native.ema_frames(x, float(self.op_mode.ema_frame))
             m = m[:, 0].unsqueeze(1)
         task_logits, features = self.predict(x, m, with_video_features=True, train=train)
@@ -661,6 +664,8 @@ class Detector(nn.Module):
         elif self.optimizer == "adamw":
             return torch.optim.AdamW(params=params, lr=lr, weight_decay=self.weight_decay)
 
+    _MEAN, _STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+
     def _transform(self, n_px):
         """CPU-side frame preprocessing of the data loader (reference :756-768); not on the hot path."""
         import torchvision.transforms as T
@@ -668,5 +673,14 @@ class Detector(nn.Module):
             T.Resize(n_px, interpolation=T.InterpolationMode.BICUBIC),
             T.CenterCrop(n_px),
             T.ConvertImageDtype(torch.float32),
-            T.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)),
+            T.Normalize(self._MEAN, self._STD),
         ])
+
+    @property
+    def transform_uint8(self):
+        """``transform`` without its last two steps: frames stay uint8 ``[..., 3, R, R]``. ``predict`` / ``forward``
+        accept such clips directly — ``ConvertImageDtype(float32)`` and ``Normalize`` then run inside the patch
+        extraction kernel (same fp32 arithmetic), and a clip crosses PCIe as 1 byte per pixel instead of 4."""
+        import torchvision.transforms as T
+        n_px = self.encoder.input_resolution
+        return T.Compose([T.Resize(n_px, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(n_px)])

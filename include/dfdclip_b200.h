@@ -83,6 +83,12 @@ int dfd_layernorm(dfd_ctx* ctx, const float* x, const float* gamma, const float*
 int dfd_patchify(dfd_ctx* ctx, const float* frames, void* out_bf16, int n_frames, int R, int patch, int Kp,
                  void* stream);
 
+/* dfd_patchify for uint8 frames [n_frames,3,R,R]: every pixel becomes (x / 255 - mean[c]) / std[c] in fp32 —
+ * T.ConvertImageDtype(torch.float32) + T.Normalize of the reference's CPU transform (src/models.py:762-768), same
+ * operation order — before the bf16 cast. mean_std: HOST array {mean[3], std[3]}. frames 8-byte aligned. */
+int dfd_patchify_u8(dfd_ctx* ctx, const uint8_t* frames, const float* mean_std, void* out_bf16, int n_frames, int R,
+                    int patch, int Kp, void* stream);
+
 /* Encoder self-attention over one packed QKV buffer (model.py:188-195): qkv bf16 [n_frames*L, 3*D]
  * (row = [q | k | v], each H x 64), no mask, softmax over keys of (q/8).k; mix bf16 [n_frames*L, D]. dh = 64. */
 int dfd_mha_fwd(dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, void* stream);
@@ -135,6 +141,14 @@ int dfd_encoder_pack_weights(dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd_v
 int dfd_encoder_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const float* frames,
                         int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
                         float* const* x_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dfd_encoder_forward on uint8 frames: the float conversion and normalisation of the data loader's transform
+ * (src/models.py:762-768) are fused into the patch extraction, so a clip crosses PCIe and HBM as 1 byte per
+ * pixel instead of 4. mean_std: HOST array {mean[3], std[3]}. */
+int dfd_encoder_forward_u8(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const uint8_t* frames,
+                           const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only,
+                           void* const* qkv_out, float* const* x_out, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Decoder: Decoder.forward / Transformer.forward / MultiheadAttention.forward (src/models.py:323-361,
