@@ -127,7 +127,8 @@ def load_library():
                                                     c_void_p, c_void_p, c_size_t, c_void_p]
         lib.dfd_decoder_attention_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                                        c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                                       c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+                                                       c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                       c_size_t, c_void_p]
         lib.dfd_adapter_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int64]
         lib.dfd_adapter_workspace_bytes.restype = c_size_t
         lib.dfd_adapter_apply.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdapterWeights), c_void_p,
@@ -326,19 +327,25 @@ def decoder_attention_train(qs, k, v, pos_emb, mask):
     return mix, stats
 
 
-def decoder_attention_backward(qs, k, v, pos_emb, mask, stats, dmix):
-    """(dqs [B,H,128], dpos_emb [T,H,64] or None) for dmix [B,H*64]; K and V are constants (frozen encoder)."""
+def decoder_attention_backward(qs, k, v, pos_emb, mask, stats, dmix, need_kv_grad=False):
+    """(dqs [B,H,128], dpos_emb [T,H,64] or None) for dmix [B,H*64]; with ``need_kv_grad`` also (dk, dv) fp32
+    [B,T,P,H,64] (trainable adapter on the taps), appended to the result."""
     b, t, p, h = _check_kv(k, v)
     lib = load_library()
     m8 = mask.to(torch.uint8).contiguous()
     dqs = torch.empty((b, h, 128), dtype=torch.float32, device=k.device)
     dpe = None if pos_emb is None else torch.empty((t, h, 64), dtype=torch.float32, device=k.device)
+    dk = torch.empty((b, t, p, h, 64), dtype=torch.float32, device=k.device) if need_kv_grad else None
+    dv = torch.empty_like(dk) if need_kv_grad else None
     nbytes = lib.dfd_decoder_attention_workspace_bytes(b, t, h)
     ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=k.device)
     check(lib.dfd_decoder_attention_backward(
         ctx(k.device), ptr(qs.contiguous()), ptr(k), ptr(v), k.stride(0), k.stride(1), k.stride(2),
         ptr(None if pos_emb is None else pos_emb.contiguous()), ptr(m8), ptr(stats.contiguous()),
-        ptr(dmix.contiguous().float()), b, t, p, h, ptr(dqs), ptr(dpe), ptr(ws), nbytes, stream_ptr(k.device)))
+        ptr(dmix.contiguous().float()), b, t, p, h, ptr(dqs), ptr(dpe), ptr(dk), ptr(dv), ptr(ws), nbytes,
+        stream_ptr(k.device)))
+    if need_kv_grad:
+        return dqs, dpe, dk, dv
     return dqs, dpe
 
 

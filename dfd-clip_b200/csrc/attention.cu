@@ -189,6 +189,7 @@ mha_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
 
 int mha_fwd_tc(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
 int mha_fwd_tc2(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
+int mha_fwd_tc3(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
 
 int mha_fwd(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream) {
   DFD_CHECK_ARG(n_frames >= 0 && L > 0 && H > 0, "mha_fwd: bad shape");
@@ -198,6 +199,9 @@ int mha_fwd(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L,
   // up to 208 tokens per frame (ViT-B/16, B/32): tcgen05 kernel; longer sequences (ViT-L/14: 257): mma.sync kernel
   // 129..208 tokens (two 128-row query tiles): pipelined two-tile kernel with P in TMEM; up to 128: one-tile kernel
   if (L > 128 && L <= 208) return mha_fwd_tc2(ctx, qkv, mix, n_frames, L, H, stream);
+  // DFD_MHA_SIMT=1 keeps the mma.sync kernel below for A/B runs
+  static const bool simt_only = getenv("DFD_MHA_SIMT") && atoi(getenv("DFD_MHA_SIMT")) != 0;
+  if (L > 208 && L <= 257 && !simt_only) return mha_fwd_tc3(ctx, qkv, mix, n_frames, L, H, stream);
   if (L <= 128) return mha_fwd_tc(ctx, qkv, mix, n_frames, L, H, stream);
   const int LP = (L + 15) & ~15;
   const int threads = (LP / 16) * 32;

@@ -1,6 +1,8 @@
 // Backward of the decoder cross-attention (src/models.py:99-146 under autograd) for the training step (config C5):
-// the encoder is frozen, so K and V are constants and the gradients that exist are those of the per-clip queries
-// (-> in_proj) and of the temporal position embedding, which is added to K and to V (:326-329).
+// the encoder is frozen, so the gradients that always exist are those of the per-clip queries (-> in_proj) and of the
+// temporal position embedding, which is added to K and to V (:326-329). With a trainable CompInvAdapter between the
+// taps and the decoder (:546-547) the per-key gradients dK, dV are needed as well: they are the two summands of the
+// position-embedding gradient and are written out on request.
 //
 // With g = dmix / 2, K~ = K + pe_t, V~ = V + pe_t, per key s and head h:
 //   gv  = g . V~                      p^ = exp(q0.K~/8 - M) / L              (M, L, o0 = sum p^ V~ saved by the forward)
@@ -33,15 +35,20 @@ dec_attn_bwd_kernel(const float* __restrict__ qs, const __nv_bfloat16* __restric
                     const __nv_bfloat16* __restrict__ vbase, int64_t stride_b, int64_t stride_t, int64_t stride_p,
                     const float* __restrict__ pos_emb, const uint8_t* __restrict__ mask,
                     const float* __restrict__ stats, const float* __restrict__ dmix, int T, int P,
-                    float* __restrict__ part) {
+                    float* __restrict__ part, float* __restrict__ dk_out, float* __restrict__ dv_out) {
   constexpr int HG = H / 4;
   constexpr int KS = (H == 4) ? 8 : (H == 8 ? 4 : (H == 12 ? 4 : 3));
   extern __shared__ float bsm[];  // [KS][H][DBW_REC]
   const int b = blockIdx.x / T, t = blockIdx.x % T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* out = part + static_cast<int64_t>(blockIdx.x) * H * DBW_REC;
+  // optional per-key gradients (trainable adapter): contiguous fp32 [B, T, P, H, 64]
+  float* dkf = dk_out ? dk_out + static_cast<int64_t>(blockIdx.x) * P * H * 64 : nullptr;
+  float* dvf = dv_out ? dv_out + static_cast<int64_t>(blockIdx.x) * P * H * 64 : nullptr;
   if (mask[b * T + t] == 0) {
     for (int i = threadIdx.x; i < H * DBW_REC; i += blockDim.x) out[i] = 0.f;
+    if (dkf)  // keys of an absent frame get no gradient
+      for (int i = threadIdx.x; i < P * H * 64; i += blockDim.x) dkf[i] = dvf[i] = 0.f;
     return;
   }
   const int hg = warp % HG, ks = warp / HG;
@@ -100,13 +107,24 @@ dec_attn_bwd_kernel(const float* __restrict__ qs, const __nv_bfloat16* __restric
     const float du = gv * G * (1.f - th * th);
     const float dy = -gv * th * G * (1.f - 0.5f * G);
     const float wv = ph + th * G;
+    float dkk[8], dvv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float diff = q1[e] - kt[e];
       const float sg = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
       dq0[e] = fmaf(ds0 * 0.125f, kt[e], dq0[e]);
       dq1[e] += 0.125f * (du * kt[e] + dy * sg);
-      dpe[e] += 0.125f * (ds0 * q0[e] + du * q1[e] - dy * sg) + wv * g[e];
+      dkk[e] = 0.125f * (ds0 * q0[e] + du * q1[e] - dy * sg);  // d/dK~ of this key
+      dvv[e] = wv * g[e];                                       // d/dV~ of this key
+      dpe[e] += dkk[e] + dvv[e];
+    }
+    if (dkf) {
+      float4* dk4 = reinterpret_cast<float4*>(dkf + (static_cast<int64_t>(p) * H + head) * 64 + d0);
+      float4* dv4 = reinterpret_cast<float4*>(dvf + (static_cast<int64_t>(p) * H + head) * 64 + d0);
+      dk4[0] = make_float4(dkk[0], dkk[1], dkk[2], dkk[3]);
+      dk4[1] = make_float4(dkk[4], dkk[5], dkk[6], dkk[7]);
+      dv4[0] = make_float4(dvv[0], dvv[1], dvv[2], dvv[3]);
+      dv4[1] = make_float4(dvv[4], dvv[5], dvv[6], dvv[7]);
     }
   }
   // ---- merge the KS key subsets
@@ -151,12 +169,16 @@ size_t dec_attn_bwd_workspace_bytes(int B, int T, int H) {
 int decoder_attention_backward(const dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                                int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask,
                                const float* stats, const float* dmix, int B, int T, int P, int H, float* dqs,
-                               float* dpos_emb, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                               float* dpos_emb, float* dk, float* dv, void* workspace, size_t workspace_bytes,
+                               cudaStream_t stream) {
   DFD_CHECK_ARG(B >= 0 && T > 0 && P > 0, "decoder_attention_backward: bad shape B=%d T=%d P=%d", B, T, P);
   if (B == 0) return 0;
   DFD_CHECK_ARG(qs && k && v && mask && stats && dmix && dqs, "decoder_attention_backward: null pointer");
   DFD_CHECK_ARG((pos_emb == nullptr) == (dpos_emb == nullptr),
                 "decoder_attention_backward: pos_emb and dpos_emb must both be given or both be NULL");
+  DFD_CHECK_ARG((dk == nullptr) == (dv == nullptr), "decoder_attention_backward: dk and dv go together");
+  DFD_CHECK_ARG(dk == nullptr || (reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) % 16 == 0,
+                "decoder_attention_backward: dk/dv must be 16-byte aligned");
   DFD_CHECK_ARG(H % 4 == 0 && H >= 4 && H <= 16, "decoder_attention_backward: heads=%d unsupported", H);
   DFD_CHECK_ARG(stride_p % 8 == 0 && stride_t % 8 == 0 && stride_b % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
@@ -179,7 +201,7 @@ int decoder_attention_backward(const dfd_ctx* ctx, const float* qs, const void* 
     }                                                                                                            \
     dec_attn_bwd_kernel<HH><<<grid, (HH / 4) * KSV * 32, smem, stream>>>(qs, kb, vb, stride_b, stride_t,         \
                                                                         stride_p, pos_emb, mask, stats, dmix, T, \
-                                                                        P, part);                                \
+                                                                        P, part, dk, dv);                        \
   } while (0)
   switch (H) {
     case 4: DFD_LAUNCH_BWD(4, 8); break;
@@ -228,11 +250,12 @@ int dfd_decoder_attention_train(dfd_ctx* ctx, const float* qs, const void* k, co
 int dfd_decoder_attention_backward(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                                    int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask,
                                    const float* stats, const float* dmix, int B, int T, int P, int H, float* dqs,
-                                   float* dpos_emb, void* workspace, size_t workspace_bytes, void* stream) {
+                                   float* dpos_emb, float* dk, float* dv, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
   dfd::clear_error();
   if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_decoder_attention_backward: ctx is NULL");
   return dfd::decoder_attention_backward(ctx, qs, k, v, stride_b, stride_t, stride_p, pos_emb, mask, stats, dmix, B, T,
-                                         P, H, dqs, dpos_emb, workspace, workspace_bytes,
+                                         P, H, dqs, dpos_emb, dk, dv, workspace, workspace_bytes,
                                          static_cast<cudaStream_t>(stream));
 }
 

@@ -108,11 +108,18 @@ class Transformer(nn.Module):
 
 class _DecoderAttentionFn(torch.autograd.Function):
     """Decoder cross-attention (reference :136-146 without the projections) with native forward and backward.
-    K and V are the frozen encoder's taps: no gradient flows into them."""
+    K and V are either the frozen encoder's taps (bf16 views, no gradient) or the output of a trainable
+    CompInvAdapter (any float dtype, ``requires_grad``): the kernels then read a bf16 copy and the backward also
+    returns dK and dV."""
 
     @staticmethod
     def forward(ctx, qs, pos_emb, k, v, mask):
         pe = None if pos_emb is None else pos_emb.detach().reshape(pos_emb.shape[0], -1, 64)
+        ctx.kv_grad = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        ctx.kv_dtypes = (k.dtype, v.dtype)
+        k, v = k.detach(), v.detach()
+        if k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+            k, v = k.to(torch.bfloat16).contiguous(), v.to(torch.bfloat16).contiguous()
         mix, stats = _native.decoder_attention_train(qs.detach(), k, v, pe, mask)
         ctx.save_for_backward(qs.detach(), stats, mask)
         ctx.kv = (k, v)
@@ -124,10 +131,14 @@ class _DecoderAttentionFn(torch.autograd.Function):
     def backward(ctx, dmix):
         qs, stats, mask = ctx.saved_tensors
         k, v = ctx.kv
-        dqs, dpe = _native.decoder_attention_backward(qs, k, v, ctx.pe, mask, stats, dmix)
+        out = _native.decoder_attention_backward(qs, k, v, ctx.pe, mask, stats, dmix, need_kv_grad=ctx.kv_grad)
+        dqs, dpe = out[0], out[1]
         if dpe is not None:
             dpe = dpe.reshape(ctx.pe_shape)
-        return dqs, dpe, None, None, None
+        dk = dv = None
+        if ctx.kv_grad:
+            dk, dv = out[2].to(ctx.kv_dtypes[0]), out[3].to(ctx.kv_dtypes[1])
+        return dqs, dpe, dk, dv, None
 
 
 class Decoder(nn.Module):
@@ -245,7 +256,7 @@ class Decoder(nn.Module):
         outs = []
         for i, (blk, kv) in enumerate(zip(self.transformer.resblocks, kvs)):
             qs = blk.attn.in_proj(blk.ln_1(x)).view(b, h, 128)
-            mix = _DecoderAttentionFn.apply(qs, self.positional_embedding, kv["k"].detach(), kv["v"].detach(), m)
+            mix = _DecoderAttentionFn.apply(qs, self.positional_embedding, kv["k"], kv["v"], m)
             x = x + blk.attn.out_proj(mix)
             x = x + blk.mlp(blk.ln_2(x))
             outs.append(x)
@@ -414,14 +425,31 @@ class CompInvAdapter(nn.Module):
         self._workspace = None
 
     # ------------------------------------------------------------------------------------------ native
+    def needs_autograd(self):
+        """True when the call must go through ``forward_autograd``: the adapter is being trained (parameters require
+        grad and grad mode is on) or its dropout layers are active."""
+        return (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())) or \
+            (self.training and self.dropout > 0)
+
     def _check_mode(self):
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("the native adapter has no dropout: call .eval() (training the adapter with "
-                                      "dropout is not implemented by the B200 path)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("gradients through the adapter (dK/dV of the decoder attention) are not "
-                                      "implemented by the B200 path: freeze the adapter (adapter.frozen=1) or run "
-                                      "under torch.no_grad()")
+        if self.needs_autograd():
+            raise NotImplementedError("the in-place native adapter is the inference / frozen path; a trainable adapter "
+                                      "(or active dropout) goes through CompInvAdapter.forward_autograd")
+
+    def forward_autograd(self, kvs):
+        """Training path (reference :921-935 under autograd): the bottleneck modules run as torch fp32 modules on the
+        tapped K/V, so their parameters (and dropout) behave exactly as in the reference's trainer; the adapted K/V
+        carry ``requires_grad`` into the decoder attention, whose native backward returns dK and dV."""
+        b, t, p, h, d = kvs[0]["k"].shape
+        out = []
+        for i, kv in enumerate(kvs):
+            new = {}
+            for name in kv:
+                x = kv[name].detach().float()
+                feat = self.layer_blocks[i][name](x.reshape(b, t, p, h * d)).view(b, t, p, h, d)
+                new[name] = x + feat if self.residual else feat
+            out.append(new)
+        return out
 
     def _gemm_weight(self, lin):
         """bf16 copy of a Linear weight for the tensor-core GEMM, rebuilt when the parameter changes."""
@@ -596,13 +624,18 @@ class Detector(nn.Module):
     def predict_from_taps(self, qkv, m, b, t, with_video_features=False, with_adapt_features=False, train=False):
         """Second half of ``predict``: adapter (in place on the taps), decoder and logit normalisation on
         already-encoded taps (``qkv[layer]`` = packed bf16 ``[B*T*L, 3D]`` buffers from ``encoder.encode``)."""
-        if self.adapter is not None:
+        adapter_autograd = self.adapter is not None and self.adapter.needs_autograd()
+        if self.adapter is not None and not adapter_autograd:
+            # inference / frozen adapter: in place on the packed taps (per-token structs commute with the patch
+            # gather below; the per-frame "nln" struct cannot be combined with patch_mask in the reference either)
             self.adapter.apply_packed(qkv, self.layer_indices, b * t, self.encoder.tokens_per_frame)  # :546-547
         kvs = self.taps_from_qkv(qkv, b, t)
         if train and "patch_mask" in self.train_mode:
             kvs = self._mask_patches(kvs)
-        if (torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters())) or \
-                (self.decoder.training and self.decoder.dropout > 0):
+        if adapter_autograd:
+            kvs = self.adapter.forward_autograd(kvs)  # :546-547 under autograd
+        if adapter_autograd or (torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters())) \
+                or (self.decoder.training and self.decoder.dropout > 0):
             # training step (or any caller that wants decoder gradients, or active dropout): differentiable decoder
             task_logits, video_features = self.decoder.run_autograd(kvs, m, logit_scale=5.0)
         else:

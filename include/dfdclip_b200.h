@@ -272,11 +272,14 @@ int dfd_decoder_attention_train(dfd_ctx* ctx, const float* qs, const void* k, co
                                 void* stream);
 
 /* Gradients of the decoder attention w.r.t. the queries (dqs fp32 [B, H, 128]) and the temporal position embedding
- * (dpos_emb fp32 [T, H, 64], NULL iff pos_emb is NULL) given dmix fp32 [B, H*64]; K and V are constants. */
+ * (dpos_emb fp32 [T, H, 64], NULL iff pos_emb is NULL) given dmix fp32 [B, H*64]. dk / dv: both NULL (frozen taps),
+ * or contiguous fp32 [B, T, P, H, 64] buffers receiving the gradients w.r.t. K and V (trainable adapter on the
+ * taps, src/models.py:546-547); keys of masked frames get zeros. */
 int dfd_decoder_attention_backward(dfd_ctx* ctx, const float* qs, const void* k, const void* v, int64_t stride_b,
                                    int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask,
                                    const float* stats, const float* dmix, int B, int T, int P, int H, float* dqs,
-                                   float* dpos_emb, void* workspace, size_t workspace_bytes, void* stream);
+                                   float* dpos_emb, float* dk, float* dv, void* workspace, size_t workspace_bytes,
+                                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -119,7 +119,10 @@ def test_patchify(cuda_device, r, patch):
 
 
 @pytest.mark.parametrize("n_frames,seq,heads", [(2, 197, 12), (3, 257, 16), (1, 16, 4), (2, 50, 12), (40, 197, 12),
-                                                (30, 129, 8), (26, 208, 12), (64, 160, 4), (2, 128, 12)])
+                                                (30, 129, 8), (26, 208, 12), (64, 160, 4), (2, 128, 12),
+                                                # attention_sm100_v3: 208 < L <= 257, several items per SM
+                                                (40, 257, 16), (21, 257, 4), (19, 256, 8), (23, 209, 12),
+                                                (17, 240, 4), (1, 257, 16)])
 def test_mha_fwd(cuda_device, n_frames, seq, heads):
     nat = _native()
     d = heads * 64

@@ -21,7 +21,14 @@ def rnd(*shape, scale=1.0, dtype=torch.bfloat16):
     return (torch.randn(*shape, generator=g) * scale).to(dev, dtype)
 
 
-if which == "mha":
+if which == "mha_l":  # ViT-L/14 shapes (config C4): 512 frames x 16 heads, 257 tokens
+    F, L, H, D = 512, 257, 16, 1024
+    M = F * L
+    qkv = rnd(M, 3 * D, scale=1.5)
+    fn = lambda: nat.mha_fwd(qkv, F, L, H)
+    flops = 4 * H * L * L * 64 * F
+    nbytes = M * 4 * D * 2
+elif which == "mha":
     qkv = rnd(M, 3 * D, scale=1.5)
     fn = lambda: nat.mha_fwd(qkv, F, L, H)
     flops = 4 * H * L * L * 64 * F
