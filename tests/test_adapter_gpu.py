@@ -160,7 +160,9 @@ def test_adapter_against_oracle_with_masks_and_host_pipeline(cuda_device):
     assert torch.equal(pipe(x.pin_memory(), m.pin_memory()), logits[0].cpu())
 
 
-def test_trainable_adapter_needs_no_grad_and_frozen_adapter_trains_decoder(cuda_device):
+def test_frozen_adapter_trains_decoder_only(cuda_device):
+    """adapter.frozen = 1 of the reference (:479-480): the native in-place adapter runs inside the training step and
+    only the decoder receives gradients. (The trainable adapter is covered by tests/test_train_gpu.py.)"""
     from dfdclip_b200 import synthetic
     arch, t, b = "tiny-256x4", 4, 3
     det, _ = build_adapter_detector(arch, t, "768-x-768-ln", cuda_device)
@@ -168,13 +170,17 @@ def test_trainable_adapter_needs_no_grad_and_frozen_adapter_trains_decoder(cuda_
     x, m = x.to(cuda_device), m.to(cuda_device)
     y = torch.tensor([0, 1, 0], device=cuda_device)
     det.train()
+    for p in det.adapter.parameters():
+        p.requires_grad = False
+    assert not det.adapter.needs_autograd()
     with torch.enable_grad():
-        with pytest.raises(NotImplementedError):
-            det(x, [y], m, train=True)
-        for p in det.adapter.parameters():  # adapter.frozen = 1 of the reference (:479-480)
-            p.requires_grad = False
         losses, logits, other = det(x, [y], m, train=True)
         losses[0].mean().backward()
     assert other == {}
     assert det.decoder.class_embedding.grad is not None and torch.isfinite(det.decoder.class_embedding.grad).all()
     assert all(p.grad is None for p in det.adapter.parameters())
+    with torch.enable_grad():
+        for p in det.adapter.parameters():
+            p.requires_grad = True
+        with pytest.raises(NotImplementedError):  # the in-place path refuses a trainable adapter under autograd
+            det.adapter.apply_packed({}, [], 0, 5)

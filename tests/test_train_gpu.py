@@ -118,3 +118,77 @@ def test_training_step_matches_oracle_autograd(cuda_device):
         opt.zero_grad()
         losses2, _, _ = det(x.to(cuda_device), [y.to(cuda_device)], m.to(cuda_device), train=True, single_task=0)
     assert losses2[0].mean().item() < loss.item()
+
+
+@pytest.mark.parametrize("b,t,p,h", [(2, 8, 196, 12), (3, 4, 50, 16), (2, 3, 17, 4)])
+def test_decoder_attention_backward_kv_grads(cuda_device, b, t, p, h):
+    """dK / dV of the decoder attention (needed by a trainable adapter on the taps, src/models.py:546-547) against
+    autograd of the fp32 restatement on the same bf16 K/V; keys of a masked frame get exactly zero."""
+    from dfdclip_b200 import _native as nat
+    g = torch.Generator(device="cpu").manual_seed(b * 7 + t)
+    d = h * 64
+    buf = torch.randn(b * t * (p + 1), 3 * d, generator=g).to(cuda_device, torch.bfloat16)
+    view = buf.view(b, t, p + 1, 3, h, 64)
+    k, v = view[:, :, 1:, 1], view[:, :, 1:, 2]
+    qs = (torch.randn(b, h, 128, generator=g) * 0.7).to(cuda_device)
+    pe = (torch.randn(t, h, 64, generator=g) * 0.3).to(cuda_device)
+    mask = torch.ones(b, t, dtype=torch.bool, device=cuda_device)
+    mask[0, -1] = False
+    dmix = torch.randn(b, d, generator=g).to(cuda_device)
+    mix, stats = nat.decoder_attention_train(qs, k, v, pe, mask)
+    dqs, dpe, dk, dv = nat.decoder_attention_backward(qs, k, v, pe, mask, stats, dmix, need_kv_grad=True)
+    dqs2, dpe2 = nat.decoder_attention_backward(qs, k, v, pe, mask, stats, dmix)
+    torch.cuda.synchronize()
+    assert torch.equal(dqs, dqs2) and torch.equal(dpe, dpe2)  # the extra outputs do not change the others
+    with torch.enable_grad():
+        k_r = k.float().clone().requires_grad_(True)
+        v_r = v.float().clone().requires_grad_(True)
+        _attention_ref(qs, k_r, v_r, pe, mask).backward(dmix)
+    for got, ref, name in ((dk, k_r.grad, "dk"), (dv, v_r.grad, "dv")):
+        assert tuple(got.shape) == (b, t, p, h, 64)
+        assert cosine(got, ref) > 0.9999, name
+        assert (got - ref).abs().max().item() < 2e-3 * max(1e-3, ref.abs().max().item()), name
+        assert got[0, -1].abs().max().item() == 0.0
+    # dpos_emb is the sum of dK and dV over clips and patches (pe is added to both, :326-329)
+    assert torch.allclose((dk + dv).sum(dim=(0, 2)), dpe, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("struct", ["768-x-768-z0", "768-x-768-nln"])
+def test_training_step_with_trainable_adapter(cuda_device, struct):
+    """The shipped training configuration: a trainable CompInvAdapter between the taps and the decoder. Adapter and
+    decoder gradients of one step against the oracle's autograd (fp32, CPU) on the same weights and clips."""
+    from dfdclip_b200 import synthetic
+    from test_adapter_gpu import build_adapter_detector
+    oracle = load_oracle()
+    arch, frames, clips = "small-512x6", 3, 4
+    det, sd = build_adapter_detector(arch, frames, struct, cuda_device)
+    det.train()
+    x, m = synthetic.make_clips(clips, frames, synthetic.vit_dims(arch)["image_size"], seed=5)
+    y = torch.tensor([0, 1, 1, 0])
+    with torch.enable_grad():
+        losses, logits, other = det(x.to(cuda_device), [y.to(cuda_device)], m.to(cuda_device), train=True,
+                                    single_task=0)
+        loss = losses[0].mean()
+        loss.backward()
+        sd_r = {k_: (v_.clone().requires_grad_(True) if not k_.startswith("encoder.") else v_) for k_, v_ in sd.items()}
+        ref_logits, _ = oracle.detector_predict(sd_r, x, m, det.layer_indices, (2,), adapter=struct)
+        ref_loss = oracle.detector_eval_losses(ref_logits, [y])[0].mean()
+        ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 3e-2
+    assert all(p.grad is None for p in det.encoder.parameters())
+    checked = {"adapter": 0, "decoder": 0}
+    for name, p in det.named_parameters():
+        if name.startswith("encoder."):
+            continue
+        ref_g = sd_r[name].grad
+        assert p.grad is not None and ref_g is not None, name
+        if ref_g.abs().max().item() < 1e-7:
+            continue
+        c = cosine(p.grad.cpu(), ref_g)
+        assert c > 0.99, (name, c)
+        checked[name.split(".")[0]] += 1
+    assert checked["adapter"] >= 4 * len(det.layer_indices) and checked["decoder"] >= 30
+    # eval mode afterwards takes the native in-place adapter and agrees with the autograd path
+    det.eval()
+    a, _ = det.predict(x.to(cuda_device), m.to(cuda_device))
+    assert (a[0] - logits[0].detach()).abs().max().item() < 2e-2
