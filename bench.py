@@ -184,7 +184,7 @@ def cpu_reference_clips_per_sec(arch, frames, clips, repeats, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    clips = 1
+    clips = args.ref_clips  # a bounded sample of the C2 batch: enough rows to keep every host core busy
     torch.set_num_threads(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dfd_oracle
@@ -208,7 +208,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 sample: %s encoder+head, %d frames/clip, %d clip per step on host CPU" % (
+        "config": {"workload": "C2 sample: %s encoder+head, %d frames/clip, %d clips per step on host CPU" % (
             args.arch, args.frames, clips), "arch": args.arch, "frames": args.frames, "clips_per_step": clips},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -340,7 +340,7 @@ def run_b200(args, rank, world, local_rank):
     achieved = gemm_flops * clips / (gemm_ms_per_step * 1e-3) / 1e12 if gemm_ms_per_step > 0 else None
     # DRAM traffic of the GEMM family per launch, from the committed ncu capture of the same step (not measured live)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
     if os.path.exists(tpath) and args.arch == "ViT-B/16" and clips == 64 and frames == 8:
         with open(tpath) as fh:
             tj = json.load(fh)
@@ -351,7 +351,7 @@ def run_b200(args, rank, world, local_rank):
         "bound": "tensor", "kernel": "gemm_bf16_2sm_kernel (tcgen05 cta_group::2, all epilogues)", "achieved": achieved,
         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
         "peak_source": "%s (sustained bf16 GEMM)" % peaks["source"], "traffic": traffic,
-        "traffic_note": "average DRAM bytes per GEMM launch (ncu capture in profiles/r1b_kernels.md)",
+        "traffic_note": "average DRAM bytes per GEMM launch (ncu capture in profiles/r1c_kernels.md)",
         "launches_per_step": gemm_launches, "ms_per_step": gemm_ms_per_step,
         "share_of_step": gemm_ms_per_step / (elapsed_ms / args.steps),
         "whole_step_tflops": total_flops * clips * world / (elapsed_ms / args.steps * 1e-3) / 1e12 / world,
@@ -360,10 +360,10 @@ def run_b200(args, rank, world, local_rank):
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, times, cores = cpu_reference_clips_per_sec(args.arch, frames, 1, repeats=4)
+        v, times, cores = cpu_reference_clips_per_sec(args.arch, frames, args.ref_clips, repeats=4)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "1 clip x %d frames, best of %d runs of the oracle port (torch fp32) of Detector.predict" % (
-                   frames, len(times))}
+               "sample": "%d clips x %d frames, best of %d runs of the oracle port (torch fp32) of Detector.predict" % (
+                   args.ref_clips, frames, len(times))}
     n_full = max(taps)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -398,6 +398,7 @@ def main():
                     "e.g. 768-x-768-nln as in the shipped configs; default: none (BASELINE config C2)")
     ap.add_argument("--taps", default=None, help="comma-separated decode_indices (decode_mode=index), e.g. "
                     "6,7,8,9,10,11 as in the shipped configs; default: stride-2 taps")
+    ap.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

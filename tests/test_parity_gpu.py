@@ -188,3 +188,34 @@ def test_predict_from_host_matches_predict(cuda_device):
     assert torch.equal(got, ref)
     again = pipe(x.pin_memory(), m.pin_memory())
     assert torch.equal(again, ref)
+
+
+@pytest.mark.gpu
+def test_full_size_c2_properties(cuda_device):
+    """BASELINE config C2 at full size (ViT-B/16, 64 clips x 8 frames): size-independent properties instead of an
+    oracle run — clips are independent units (a sub-batch reproduces its rows bit-exactly), reruns are bit-identical,
+    masked frames do not matter, logits have norm 5, and the video-level mean of probabilities (inference.py:121,140)
+    equals the per-clip softmax averaged by hand."""
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.inference import video_mean_probs
+    det, _ = build_detector("ViT-B/16", 8, [0, 2, 4, 6, 8, 10], cuda_device)
+    x, m = synthetic.make_clips(64, 8, 224, seed=7)
+    x, m = x.to(cuda_device), m.to(cuda_device)
+    assert not m.all()
+    full, _ = det.predict(x, m)
+    again, _ = det.predict(x, m)
+    part, _ = det.predict(x[20:29], m[20:29])
+    x2 = x.clone()
+    x2[~m] = -7.0
+    masked, _ = det.predict(x2, m)
+    torch.cuda.synchronize()
+    assert torch.isfinite(full[0]).all()
+    assert torch.equal(full[0], again[0])
+    assert torch.equal(full[0][20:29], part[0])
+    assert torch.equal(full[0], masked[0])
+    assert torch.allclose(full[0].norm(dim=-1), torch.full((64,), 5.0, device=cuda_device), atol=1e-3)
+    counts = [10, 30, 24]
+    scores = video_mean_probs(full[0], counts)
+    probs = full[0].softmax(-1)
+    assert torch.allclose(scores[1], probs[10:40].mean(0), atol=1e-6)
+    assert torch.allclose(scores.sum(-1), torch.ones(3, device=cuda_device), atol=1e-5)
