@@ -27,7 +27,7 @@ EXPORTS = (
     "dfd_decoder_attention_workspace_bytes", "dfd_decoder_attention_train", "dfd_decoder_attention_backward",
     "dfd_adapter_workspace_bytes", "dfd_adapter_apply", "dfd_ema_frames",
     "dfd_decoder_attention_modes_workspace_bytes", "dfd_decoder_attention_modes",
-    "dfd_patchify_u8", "dfd_encoder_forward_u8",
+    "dfd_patchify_u8", "dfd_encoder_forward_u8", "dfd_gemm_bf16_ln",
 )
 
 
@@ -65,6 +65,14 @@ ATTN_FRAME, ATTN_TEMPORAL = 1, 2
 
 class KvTaps(ctypes.Structure):
     _fields_ = [("k", _PP), ("v", _PP), ("stride_b", c_int64), ("stride_t", c_int64), ("stride_p", c_int64)]
+
+
+class GemmLnArgs(ctypes.Structure):
+    _fields_ = [("stats_in", c_void_p), ("colsum", c_void_p), ("slots", c_int), ("stats_out", c_void_p),
+                ("bf16_out", c_void_p), ("ld_bf16", c_int64)]
+
+
+EPI_STORE_BF16_LNFOLD, EPI_STORE_BF16_QGELU_LNFOLD, EPI_RESID_LN_F32 = 6, 7, 8
 
 
 class AdapterWeights(ctypes.Structure):
@@ -105,6 +113,8 @@ def load_library():
                                                  c_void_p, c_void_p]
         lib.dfd_encoder_forward.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p, c_int, c_int,
                                             c_int, _PP, _PP, c_void_p, c_size_t, c_void_p]
+        lib.dfd_gemm_bf16_ln.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                         c_int, c_int, c_int, c_int, ctypes.POINTER(GemmLnArgs), c_void_p]
         lib.dfd_patchify_u8.argtypes = [c_void_p, c_void_p, ctypes.POINTER(c_float), c_void_p, c_int, c_int, c_int,
                                         c_int, c_void_p]
         lib.dfd_encoder_forward_u8.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p,
@@ -217,6 +227,32 @@ def gemm_bf16(a, w, bias, out, epilogue):
     n = w.shape[0]
     check(load_library().dfd_gemm_bf16(ctx(a.device), ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out),
                                        out.stride(0), m, n, k, epilogue, stream_ptr(a.device)))
+    return out
+
+
+def gemm_resid_ln(a, w, bias, x):
+    """x (fp32, in place) += a @ w^T + bias on the SM-pair kernel; returns (bf16 copy of the new x, per-row partial
+    statistics [M, 2*N/256, 2]) for a LayerNorm-folded consumer GEMM."""
+    m, k = a.shape
+    n = w.shape[0]
+    xb = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    stats = torch.empty((m, 2 * n // 256, 2), dtype=torch.float32, device=a.device)
+    args = GemmLnArgs(None, None, 0, stats.data_ptr(), xb.data_ptr(), xb.stride(0))
+    check(load_library().dfd_gemm_bf16_ln(ctx(a.device), ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(x),
+                                          x.stride(0), m, n, k, EPI_RESID_LN_F32, ctypes.byref(args),
+                                          stream_ptr(a.device)))
+    return xb, stats
+
+
+def gemm_lnfold(xb, stats, w_folded, colsum, bias_folded, out, quickgelu=False):
+    """out (bf16) = [quickgelu](rstd * (xb @ w_folded^T - mu * colsum) + bias_folded), mu / rstd from `stats`."""
+    m, k = xb.shape
+    n = w_folded.shape[0]
+    args = GemmLnArgs(stats.data_ptr(), colsum.data_ptr(), stats.shape[1], None, None, 0)
+    check(load_library().dfd_gemm_bf16_ln(
+        ctx(xb.device), ptr(xb), xb.stride(0), ptr(w_folded), w_folded.stride(0), ptr(bias_folded), ptr(out),
+        out.stride(0), m, n, k, EPI_STORE_BF16_QGELU_LNFOLD if quickgelu else EPI_STORE_BF16_LNFOLD,
+        ctypes.byref(args), stream_ptr(xb.device)))
     return out
 
 

@@ -16,7 +16,8 @@
 namespace dfd {
 
 int layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int pos_period, void* out_bf16,
-              float* out_f32, int64_t rows, int D, cudaStream_t stream);
+              float* out_f32, int64_t rows, int D, cudaStream_t stream, void* fold_bf16 = nullptr,
+              float* fold_stats = nullptr, int slots = 0);
 
 // ------------------------------------------------------------------------------ decoder attention (partial)
 constexpr int DEC_REC = 130;  // per (clip, frame, head): m, l, acc0[64], acc1[64]

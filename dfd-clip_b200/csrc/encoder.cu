@@ -11,17 +11,37 @@
 //   patches bf16 [M, Kp]   im2col of the frames (cls rows zero) = A operand of the patch-embedding GEMM
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
 
 namespace dfd {
 
 int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
               void* out, int64_t ldo, int M, int N, int K, int epilogue, cudaStream_t stream);
 int layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int pos_period, void* out_bf16,
-              float* out_f32, int64_t rows, int D, cudaStream_t stream);
+              float* out_f32, int64_t rows, int D, cudaStream_t stream, void* fold_bf16 = nullptr,
+              float* fold_stats = nullptr, int slots = 0);
 int patchify(const void* frames, void* out, int n_frames, int R, int patch, int Kp, cudaStream_t stream,
              const float* mean_std);
 int mha_fwd(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, int L, int H, cudaStream_t stream);
 int cast_pad_bf16(const float* src, void* dst, int64_t rows, int cols, int dst_ld, cudaStream_t stream);
+int gemm_bf16_ln(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                 void* out, int64_t ldo, int M, int N, int K, int epilogue, const dfd_gemm_ln_args* a,
+                 cudaStream_t stream);
+int fold_ln_linear(const float* W, const float* bias, const float* gamma, const float* beta, void* wf, float* colsum,
+                   float* bias_f, int N, int K, cudaStream_t stream);
+
+// LayerNorm folded into the GEMMs around it (see dfd_gemm_bf16_ln; the folding epilogues live in the SM-pair kernel,
+// which then runs for every M so that results do not depend on the batch size). OPT-IN with DFD_LN_FUSE=1: measured
+// on the power-capped B200 the removed LayerNorm passes (-1.65 ms per C2 step) are almost entirely paid back by the
+// heavier GEMM epilogues (+1.0 .. +1.4 ms), the step moves by 0 .. 1.7 %, so the separate
+// LayerNorm kernels stay the default.
+static bool ln_fuse_enabled() {
+  static const bool v = []() {
+    const char* e = getenv("DFD_LN_FUSE");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return v;
+}
 
 static inline size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
@@ -54,6 +74,8 @@ struct PackedLayout {
   // within a layer
   size_t w_in, w_out, w_fc, w_proj;  // bf16
   size_t b_in, b_out, b_fc, b_proj, ln1_w, ln1_b, ln2_w, ln2_b;  // fp32
+  // LayerNorm-folded copies: bf16 (gamma . W), fp32 column sums of it, fp32 b + W beta
+  size_t wf_in, wf_fc, c_in, c_fc, bf_in, bf_fc;
   size_t total;
 };
 
@@ -81,13 +103,21 @@ static PackedLayout packed_layout(const VitShape& s) {
   p.ln1_b = ltake(D * 4);
   p.ln2_w = ltake(D * 4);
   p.ln2_b = ltake(D * 4);
+  if (ln_fuse_enabled()) {  // the folded copies exist only when the opt-in path is selected
+    p.wf_in = ltake(3 * D * D * 2);
+    p.wf_fc = ltake(4 * D * D * 2);
+    p.c_in = ltake(3 * D * 4);
+    p.c_fc = ltake(4 * D * 4);
+    p.bf_in = ltake(3 * D * 4);
+    p.bf_fc = ltake(4 * D * 4);
+  }
   p.layer_stride = lo;
   p.total = p.layer0 + p.layer_stride * s.layers;
   return p;
 }
 
 struct EncWs {
-  size_t x, u, mix, hid, qkv, patches, total;
+  size_t x, u, mix, hid, qkv, patches, stats, total;
 };
 
 static EncWs enc_ws(const VitShape& s, int n_frames) {
@@ -101,6 +131,7 @@ static EncWs enc_ws(const VitShape& s, int n_frames) {
   w.hid = take(M * 4 * D * 2);   // also hosts the patch matrix before layer 0 (Kp <= 4D)
   w.qkv = take(M * 3 * D * 2);   // scratch QKV for layers whose taps are not requested
   w.patches = w.hid;
+  w.stats = take(M * (2 * D / 256) * 2 * 4);  // per row and 128-column block: (sum, sum of squares) of x
   w.total = off;
   return w;
 }
@@ -148,6 +179,14 @@ int encoder_pack_weights(const dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd
     DFD_TRY(copy_f32(lb + pl.ln1_b, w->ln_1_bias[l], D));
     DFD_TRY(copy_f32(lb + pl.ln2_w, w->ln_2_weight[l], D));
     DFD_TRY(copy_f32(lb + pl.ln2_b, w->ln_2_bias[l], D));
+    if (!ln_fuse_enabled()) continue;
+    // ln_1 folded into in_proj, ln_2 folded into c_fc
+    DFD_TRY(fold_ln_linear(w->in_proj_weight[l], w->in_proj_bias[l], w->ln_1_weight[l], w->ln_1_bias[l],
+                           base + lb + pl.wf_in, reinterpret_cast<float*>(base + lb + pl.c_in),
+                           reinterpret_cast<float*>(base + lb + pl.bf_in), 3 * s.D, s.D, stream));
+    DFD_TRY(fold_ln_linear(w->c_fc_weight[l], w->c_fc_bias[l], w->ln_2_weight[l], w->ln_2_bias[l],
+                           base + lb + pl.wf_fc, reinterpret_cast<float*>(base + lb + pl.c_fc),
+                           reinterpret_cast<float*>(base + lb + pl.bf_fc), 4 * s.D, s.D, stream));
   }
   (void)ctx;
   return 0;
@@ -190,8 +229,45 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
   DFD_TIMED(DFD_TAG_PATCHIFY, patchify(frames, patches, n_frames, s.R, s.p, s.Kp, stream, mean_std));
   DFD_TIMED(DFD_TAG_GEMM_PATCH,
             gemm_bf16(ctx, patches, s.Kp, pk + pl.conv_w, s.Kp, nullptr, x, D, M, D, s.Kp, DFD_EPI_STORE_F32, stream));
-  DFD_TIMED(DFD_TAG_LAYERNORM,
-            layernorm(x, f32p(pl.ln_pre_w), f32p(pl.ln_pre_b), f32p(pl.posc), s.L, nullptr, x, M, D, stream));
+  // LayerNorm folded into the GEMMs: x's producers (ln_pre here, then every residual GEMM) also emit bf16(x) into `u`
+  // and per-row partial statistics into `stats`; ln_1 / ln_2 are finished in the QKV / c_fc epilogues.
+  const bool fuse = ln_fuse_enabled() && D <= 1024;
+  float* stats = reinterpret_cast<float*>(ws + wl.stats);
+  const int slots = 2 * D / 256;
+  if (fuse) {
+    DFD_TIMED(DFD_TAG_LAYERNORM, layernorm(x, f32p(pl.ln_pre_w), f32p(pl.ln_pre_b), f32p(pl.posc), s.L, nullptr, x, M,
+                                           D, stream, u, stats, slots));
+  } else {
+    DFD_TIMED(DFD_TAG_LAYERNORM,
+              layernorm(x, f32p(pl.ln_pre_w), f32p(pl.ln_pre_b), f32p(pl.posc), s.L, nullptr, x, M, D, stream));
+  }
+  dfd_gemm_ln_args fold_in{};   // consumer side: statistics + column sums
+  fold_in.stats_in = stats;
+  fold_in.slots = slots;
+  dfd_gemm_ln_args resid{};     // producer side: residual update that refreshes u and the statistics
+  resid.stats_out = stats;
+  resid.bf16_out = u;
+  resid.ld_bf16 = D;
+
+  for (int l = 0; l < num_run_layers && fuse; ++l) {
+    const size_t lb = pl.layer0 + pl.layer_stride * l;
+    void* qkv = (qkv_out && qkv_out[l]) ? qkv_out[l] : static_cast<void*>(ws + wl.qkv);
+    fold_in.colsum = f32p(lb + pl.c_in);
+    DFD_TIMED(DFD_TAG_GEMM_QKV, gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_in, D, f32p(lb + pl.bf_in), qkv, 3 * D, M,
+                                             3 * D, D, DFD_EPI_STORE_BF16_LNFOLD, &fold_in, stream));
+    if (l == num_run_layers - 1 && last_qkv_only) break;
+    DFD_TIMED(DFD_TAG_MHA, mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
+    DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16_ln(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
+                                             DFD_EPI_RESID_LN_F32, &resid, stream));
+    fold_in.colsum = f32p(lb + pl.c_fc);
+    DFD_TIMED(DFD_TAG_GEMM_FC, gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_fc, D, f32p(lb + pl.bf_fc), hid, 4 * D, M,
+                                            4 * D, D, DFD_EPI_STORE_BF16_QGELU_LNFOLD, &fold_in, stream));
+    DFD_TIMED(DFD_TAG_GEMM_PROJ, gemm_bf16_ln(ctx, hid, 4 * D, pk + lb + pl.w_proj, 4 * D, f32p(lb + pl.b_proj), x, D,
+                                              M, D, 4 * D, DFD_EPI_RESID_LN_F32, &resid, stream));
+    if (x_out && x_out[l])
+      DFD_CUDA_OK(cudaMemcpyAsync(x_out[l], x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (fuse) return 0;
 
   for (int l = 0; l < num_run_layers; ++l) {
     const size_t lb = pl.layer0 + pl.layer_stride * l;

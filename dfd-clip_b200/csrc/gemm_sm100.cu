@@ -245,6 +245,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // Cross-CTA signalling: TMA loads of both CTAs complete_tx on the LEADER's full barrier; tcgen05.commit
 // multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps
 // arrive remotely on the leader's "accumulator drained" barrier.
+constexpr int DFD_EPI_RESID_LN_F32_X2 = 9;  // internal second instance of DFD_EPI_RESID_LN_F32 (see gemm2::Cfg)
+
 namespace gemm2 {
 constexpr int BM = 128;            // rows per CTA (256 per cluster)
 constexpr int BN = 256;
@@ -258,15 +260,40 @@ constexpr int OUT_BUF = 32 * 128;
 constexpr int OUT_BUFS_PER_WARP = 2;
 constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each draining one 128-column half of the tile
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
-constexpr int OFF_OUT = OFF_B + STAGES * B_STAGE;
-constexpr int OFF_BAR = OFF_OUT + EPI_WARPS * OUT_BUFS_PER_WARP * OUT_BUF;
-constexpr int NUM_BARS = 2 * STAGES + 4;
-constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
-constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
 constexpr uint32_t TMEM_COLS = 512;
+
+// Shared-memory plan. The residual + LayerNorm-statistics epilogue stages fp32 boxes of x (TMA load, update in place,
+// TMA store) and one bf16 box per epilogue warp, with one load barrier per fp32 box. Two instances, picked by K:
+//   DFD_EPI_RESID_LN_F32      5-stage operand ring, ONE fp32 box: for long K (c_proj, K = 4D) the epilogue has slack
+//                             but a 4-stage ring cost the mainloop 12 %;
+//   DFD_EPI_RESID_LN_F32_X2   4-stage ring, TWO fp32 boxes (the next box of x is in flight while one is updated): for
+//                             short K (out_proj) the epilogue is the critical path (single box: 245 vs 208 us).
+template <int EPI>
+struct Cfg {
+  static constexpr bool kResidLn = (EPI == DFD_EPI_RESID_LN_F32 || EPI == DFD_EPI_RESID_LN_F32_X2);
+  static constexpr int NX = (EPI == DFD_EPI_RESID_LN_F32_X2) ? 2 : 1;   // fp32 boxes of x per epilogue warp
+  static constexpr int STAGES = (EPI == DFD_EPI_RESID_LN_F32_X2) ? 4 : gemm2::STAGES;
+  static constexpr int OUT_BUFS_PER_WARP = kResidLn ? NX + 1 : gemm2::OUT_BUFS_PER_WARP;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + STAGES * A_STAGE;
+  static constexpr int OFF_OUT = OFF_B + STAGES * B_STAGE;
+  static constexpr int OFF_BAR = OFF_OUT + EPI_WARPS * OUT_BUFS_PER_WARP * OUT_BUF;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + (kResidLn ? 2 * EPI_WARPS : 0);  // + x-load barriers
+  static constexpr int OFF_TMEM_PTR = OFF_BAR + NUM_BARS * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;
+  static_assert(SMEM_BYTES <= 227 * 1024, "2-SM GEMM shared memory exceeds the per-CTA limit");
+};
 }  // namespace gemm2
+
+// Arguments of the LayerNorm-folding epilogues (device pointers; see dfd_gemm_ln_args in the header).
+struct GemmLnArgs {
+  const float* stats_in = nullptr;  // [M, slots, 2] partial (sum, sum of squares) of the rows whose bf16 copy is A
+  const float* colsum = nullptr;    // [N] c[n] = sum_k W'[n, k]
+  float* stats_out = nullptr;       // RESID_LN: [M, 2 * N / 256, 2]
+  const float* x = nullptr;         // RESID_LN: the fp32 rows being updated (= out), read with plain loads
+  int64_t ldx = 0;
+  int slots = 0;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -318,8 +345,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2::THREADS, 1)
 gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmU,
+                     const float* __restrict__ bias, const GemmLnArgs ln, int M, int N, int K) {
   using namespace gemm2;
+  using C = Cfg<EPI>;
+  constexpr int STAGES = C::STAGES, OUT_BUFS_PER_WARP = C::OUT_BUFS_PER_WARP;
+  constexpr int OFF_A = C::OFF_A, OFF_B = C::OFF_B, OFF_OUT = C::OFF_OUT, OFF_BAR = C::OFF_BAR,
+                OFF_TMEM_PTR = C::OFF_TMEM_PTR;
+  constexpr bool kLnFold = (EPI == DFD_EPI_STORE_BF16_LNFOLD || EPI == DFD_EPI_STORE_BF16_QGELU_LNFOLD);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -345,6 +378,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if constexpr (C::kResidLn) tma_prefetch_desc(&tmU);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -356,6 +390,8 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_init(&tmem_full[a], 1);
         mbar_init(&tmem_empty[a], 2 * EPI_WARPS);  // one elected arrival per epilogue warp of both CTAs
       }
+      if constexpr (C::kResidLn)
+        for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&tmem_empty[2 + i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -421,6 +457,115 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int q = warp & 3;
     const int ew = warp - 2;
     uint8_t* obuf = smem + OFF_OUT + ew * (OUT_BUFS_PER_WARP * OUT_BUF);
+    if constexpr (C::kResidLn) {
+      // ---- x = x + acc + bias with the FULL value in hand (instead of a blind reduce-add), so that the same pass
+      // also emits the bf16 copy of x (the A operand of the next, LayerNorm-folded GEMM) and each row's partial
+      // (sum, sum of squares) over this warp's 128 columns. LayerNorm itself then costs no pass over x at all:
+      // LN(x) W^T = rstd (x (gamma.W)^T - mu c) + (b + W beta) is finished in the consumer GEMM's epilogue.
+      const int half = ew >> 2;
+      constexpr int NX = C::NX;
+      uint8_t* xbuf = obuf;                   // NX fp32 boxes (32 rows x 32 cols): TMA load of x, update in place, TMA store
+      uint8_t* ubuf = obuf + NX * OUT_BUF;    // bf16 staging box (32 rows x 64 cols), filled by two fp32 boxes
+      uint64_t* lbar = tmem_empty + 2 + 2 * ew;
+      uint32_t lphase = 0;                    // bit i = parity of lbar[i]
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + q * 32;
+        const int row = row0 + lane;
+        const bool live = row0 < M;          // a warp whose 32 rows lie beyond M only drains its accumulator
+        const int col_base = n_blk * BN + half * 128;
+        // the first box(es) of x are fetched while the MMAs of this tile are still running
+        if (lane == 0 && live) {
+          tma_store_wait_read<0>();          // the previous tile's last stores have left shared memory
+#pragma unroll
+          for (int b = 0; b < NX; ++b) {
+            mbar_arrive_expect_tx(&lbar[b], OUT_BUF);
+            tma_load_2d(&tmC, &lbar[b], xbuf + b * OUT_BUF, col_base + b * 32, row0, kEvictFirst);
+          }
+        }
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * 128;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int xi = b % NX;
+          const int c = col_base + b * 32;
+          uint32_t r[32];
+          tmem_ld32(t_row + b * 32, r);
+          uint8_t* xdst = xbuf + xi * OUT_BUF + lane * 128;
+          uint8_t* udst = ubuf + lane * 128;
+          float v[32];
+          if (live) {
+            mbar_wait(&lbar[xi], (lphase >> xi) & 1u);
+            lphase ^= 1u << xi;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const float4 xv = *reinterpret_cast<const float4*>(xdst + ((ch ^ (lane & 7)) << 4));
+              v[4 * ch] = xv.x; v[4 * ch + 1] = xv.y; v[4 * ch + 2] = xv.z; v[4 * ch + 3] = xv.w;
+            }
+          }
+          tmem_ld_wait();
+          if (b == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+          }
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c) + j) : make_float4(0, 0, 0, 0);
+              v[4 * j + 0] += __uint_as_float(r[4 * j + 0]) + b4.x;
+              v[4 * j + 1] += __uint_as_float(r[4 * j + 1]) + b4.y;
+              v[4 * j + 2] += __uint_as_float(r[4 * j + 2]) + b4.z;
+              v[4 * j + 3] += __uint_as_float(r[4 * j + 3]) + b4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s1 += v[j];
+              s2 = fmaf(v[j], v[j], s2);
+            }
+            // lane 0 has waited for every earlier store group before it issued a refill: past this point ubuf (last
+            // stored one box ago) and this fp32 box are free
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 f = make_uint4(__float_as_uint(v[4 * ch]), __float_as_uint(v[4 * ch + 1]),
+                                         __float_as_uint(v[4 * ch + 2]), __float_as_uint(v[4 * ch + 3]));
+              *reinterpret_cast<uint4*>(xdst + ((ch ^ (lane & 7)) << 4)) = f;
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const uint4 h = make_uint4(pack_bf16(v[8 * ch], v[8 * ch + 1]), pack_bf16(v[8 * ch + 2], v[8 * ch + 3]),
+                                         pack_bf16(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16(v[8 * ch + 6], v[8 * ch + 7]));
+              *reinterpret_cast<uint4*>(udst + ((((b & 1) * 4 + ch) ^ (lane & 7)) << 4)) = h;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, xbuf + xi * OUT_BUF, c, row0);
+              if (b & 1) tma_store_2d(&tmU, ubuf, col_base + (b >> 1) * 64, row0);
+              tma_store_commit();
+              // refill this fp32 box with box b + NX once its store has read it; with two boxes the wait after the odd
+              // box is still needed: it frees ubuf for the next even box
+              if (b + NX < 4 || (NX == 2 && b == 1)) tma_store_wait_read<0>();
+              if (b + NX < 4) {
+                mbar_arrive_expect_tx(&lbar[xi], OUT_BUF);
+                tma_load_2d(&tmC, &lbar[xi], xbuf + xi * OUT_BUF, c + NX * 32, row0, kEvictFirst);
+              }
+            }
+          }
+        }
+        if (live && row < M)
+          *reinterpret_cast<float2*>(ln.stats_out + (static_cast<int64_t>(row) * ln.slots + n_blk * 2 + half) * 2) =
+              make_float2(s1, s2);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (lane == 0) tma_store_wait_all<0>();
+    } else {
     constexpr bool kOutF32 = (EPI == DFD_EPI_STORE_F32 || EPI == DFD_EPI_ADD_F32);
     constexpr int COLS_PER_BOX = kOutF32 ? 32 : 64;
     constexpr int NUM_BOX = BN / COLS_PER_BOX;
@@ -429,10 +574,40 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
+    float2 ln_pref[8];  // (sum, sum of squares) partials of one row, at most 8 blocks of 128 columns (D <= 1024)
+    auto load_ln_partials = [&](int row) {
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl)
+        ln_pref[sl] = (kLnFold && row < M && sl < ln.slots)
+                          ? reinterpret_cast<const float2*>(ln.stats_in)[static_cast<int64_t>(row) * ln.slots + sl]
+                          : make_float2(0.f, 0.f);
+    };
+    if constexpr (kLnFold) {
+      if (cluster_id < num_tiles)
+        load_ln_partials((cluster_id / num_n) * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane);
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row0 = m_blk * 2 * BM + static_cast<int>(rank) * BM + q * 32;
       const int col0 = n_blk * BN;
+      // LayerNorm folded into this GEMM: A is the bf16 copy of the un-normalised rows and W carries gamma, so
+      // out = rstd * (acc - mu * colsum[n]) + bias'[n]; mu / rstd come from the producer's per-row partial sums.
+      float ln_mu = 0.f, ln_rstd = 0.f;
+      if constexpr (kLnFold) {
+        // the partial sums of this tile's row were requested one tile ago (ln_pref); request the next tile's now, so
+        // that the dependent global loads never sit on the epilogue's critical path
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) {
+          a1 += ln_pref[sl].x;
+          a2 += ln_pref[sl].y;
+        }
+        const float inv_k = 1.0f / static_cast<float>(K);
+        ln_mu = a1 * inv_k;
+        ln_rstd = rsqrtf(fmaxf(a2 * inv_k - ln_mu * ln_mu, 0.f) + 1e-5f);
+        const int next = tile + num_clusters;
+        if (next < num_tiles) load_ln_partials((next / num_n) * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -462,11 +637,20 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int j = 0; j < 32; j += 4) {
               float4 b4 =
                   bias ? __ldg(reinterpret_cast<const float4*>(bias + c + half * 32 + j)) : make_float4(0, 0, 0, 0);
-              float v0 = __uint_as_float(r[j + 0]) + b4.x;
-              float v1 = __uint_as_float(r[j + 1]) + b4.y;
-              float v2 = __uint_as_float(r[j + 2]) + b4.z;
-              float v3 = __uint_as_float(r[j + 3]) + b4.w;
-              if constexpr (EPI == DFD_EPI_STORE_BF16_QGELU) {
+              float v0, v1, v2, v3;
+              if constexpr (kLnFold) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(ln.colsum + c + half * 32 + j));
+                v0 = fmaf(ln_rstd, fmaf(-ln_mu, c4.x, __uint_as_float(r[j + 0])), b4.x);
+                v1 = fmaf(ln_rstd, fmaf(-ln_mu, c4.y, __uint_as_float(r[j + 1])), b4.y);
+                v2 = fmaf(ln_rstd, fmaf(-ln_mu, c4.z, __uint_as_float(r[j + 2])), b4.z);
+                v3 = fmaf(ln_rstd, fmaf(-ln_mu, c4.w, __uint_as_float(r[j + 3])), b4.w);
+              } else {
+                v0 = __uint_as_float(r[j + 0]) + b4.x;
+                v1 = __uint_as_float(r[j + 1]) + b4.y;
+                v2 = __uint_as_float(r[j + 2]) + b4.z;
+                v3 = __uint_as_float(r[j + 3]) + b4.w;
+              }
+              if constexpr (EPI == DFD_EPI_STORE_BF16_QGELU || EPI == DFD_EPI_STORE_BF16_QGELU_LNFOLD) {
                 v0 = quick_gelu_fast(v0);
                 v1 = quick_gelu_fast(v1);
                 v2 = quick_gelu_fast(v2);
@@ -511,6 +695,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (acc == 0) acc_phase ^= 1;
     }
     if (lane == 0) tma_store_wait_all<0>();
+    }  // generic epilogues
   }
 
   // no CTA of the pair may exit (or free TMEM) while the other can still signal it or read its shared memory
@@ -539,18 +724,19 @@ static int launch(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap&
 
 template <int EPI>
 static int launch2(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                   const float* bias, int M, int N, int K, cudaStream_t stream) {
+                   const float* bias, int M, int N, int K, cudaStream_t stream, const CUtensorMap* tmU = nullptr,
+                   const GemmLnArgs& ln = GemmLnArgs()) {
   using namespace gemm2;
+  constexpr int SMEM = Cfg<EPI>::SMEM_BYTES;
   static bool configured[64] = {};
   if (!configured[ctx->device & 63]) {
-    DFD_CUDA_OK(
-        cudaFuncSetAttribute(gemm_bf16_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DFD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured[ctx->device & 63] = true;
   }
   const int num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
   const int max_clusters = ctx->num_sms / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  gemm_bf16_2sm_kernel<EPI><<<2 * clusters, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, bias, M, N, K);
+  gemm_bf16_2sm_kernel<EPI><<<2 * clusters, THREADS, SMEM, stream>>>(tmA, tmB, tmC, tmU ? *tmU : tmC, bias, ln, M, N, K);
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -623,7 +809,65 @@ int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int
   }
 }
 
+// GEMMs with LayerNorm folded around them (2-SM kernel only, M > 128):
+//   DFD_EPI_RESID_LN_F32            out_f32 (= ln->x) += acc + bias; also writes bf16(out) and per-row partial statistics
+//   DFD_EPI_STORE_BF16[_QGELU]_LNFOLD  out_bf16 = [quickgelu] (rstd * (acc - mu * colsum[n]) + bias[n])
+int gemm_bf16_ln(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                 void* out, int64_t ldo, int M, int N, int K, int epilogue, const dfd_gemm_ln_args* a,
+                 cudaStream_t stream) {
+  using namespace gemm;
+  DFD_CHECK_ARG(ctx && A && W && out && a, "gemm_ln: null pointer");
+  DFD_CHECK_ARG(M > 0, "gemm_ln: empty problem");
+  DFD_CHECK_ARG(N > 0 && K > 0 && N % BN == 0, "gemm_ln: N=%d must be a positive multiple of %d", N, BN);
+  DFD_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K && ldo >= N,
+                "gemm_ln: bad K / leading dimensions");
+  DFD_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+                "gemm_ln: operands must be 16-byte aligned");
+  DFD_CHECK_ARG(bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0, "gemm_ln: bias must be 16-byte aligned");
+  CUtensorMap tmA, tmB, tmC, tmU;
+  DFD_TRY(make_tmap_2d(ctx, &tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, BM, BK));
+  DFD_TRY(make_tmap_2d(ctx, &tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, gemm2::BNH, BK));
+  GemmLnArgs ln;
+  if (epilogue == DFD_EPI_RESID_LN_F32) {
+    DFD_CHECK_ARG(a->stats_out && a->bf16_out, "gemm_ln: RESID_LN needs stats_out and bf16_out");
+    DFD_CHECK_ARG(ldo % 4 == 0 && a->ld_bf16 % 8 == 0 && a->ld_bf16 >= N &&
+                      reinterpret_cast<uintptr_t>(a->bf16_out) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(a->stats_out) % 8 == 0,
+                  "gemm_ln: RESID_LN alignment");
+    DFD_TRY(make_tmap_2d(ctx, &tmC, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldo, 32, 32));
+    DFD_TRY(make_tmap_2d(ctx, &tmU, a->bf16_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, a->ld_bf16, 32, 64));
+    ln.stats_out = a->stats_out;
+    ln.x = static_cast<const float*>(out);
+    ln.ldx = ldo;
+    ln.slots = 2 * (N / BN);
+    if (K <= 1024) return launch2<DFD_EPI_RESID_LN_F32_X2>(ctx, tmA, tmB, tmC, bias, M, N, K, stream, &tmU, ln);
+    return launch2<DFD_EPI_RESID_LN_F32>(ctx, tmA, tmB, tmC, bias, M, N, K, stream, &tmU, ln);
+  }
+  DFD_CHECK_ARG(epilogue == DFD_EPI_STORE_BF16_LNFOLD || epilogue == DFD_EPI_STORE_BF16_QGELU_LNFOLD,
+                "gemm_ln: unknown epilogue %d", epilogue);
+  DFD_CHECK_ARG(a->stats_in && a->colsum && a->slots > 0 && a->slots <= 8,
+                "gemm_ln: LNFOLD needs stats_in, colsum and 1..8 slots");
+  DFD_CHECK_ARG(ldo % 8 == 0 && reinterpret_cast<uintptr_t>(a->colsum) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(a->stats_in) % 8 == 0,
+                "gemm_ln: LNFOLD alignment");
+  DFD_TRY(make_tmap_2d(ctx, &tmC, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldo, 32, 64));
+  ln.stats_in = a->stats_in;
+  ln.colsum = a->colsum;
+  ln.slots = a->slots;
+  if (epilogue == DFD_EPI_STORE_BF16_LNFOLD)
+    return launch2<DFD_EPI_STORE_BF16_LNFOLD>(ctx, tmA, tmB, tmC, bias, M, N, K, stream, nullptr, ln);
+  return launch2<DFD_EPI_STORE_BF16_QGELU_LNFOLD>(ctx, tmA, tmB, tmC, bias, M, N, K, stream, nullptr, ln);
+}
+
 }  // namespace dfd
+
+extern "C" int dfd_gemm_bf16_ln(dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw,
+                                const float* bias, void* out, int64_t ldo, int M, int N, int K, int epilogue,
+                                const dfd_gemm_ln_args* args, void* stream) {
+  dfd::clear_error();
+  return dfd::gemm_bf16_ln(ctx, A, lda, W, ldw, bias, out, ldo, M, N, K, epilogue, args,
+                           static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int dfd_gemm_bf16(dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                              void* out, int64_t ldo, int M, int N, int K, int epilogue, void* stream) {

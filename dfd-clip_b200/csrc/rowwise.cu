@@ -11,10 +11,15 @@ namespace dfd {
 // One warp per row; the row lives in registers (VEC float4 per lane, D = 128 * VEC).
 // Reference: LayerNorm.forward src/clip/model.py:157-163 (fp32 math, eps 1e-5, biased variance);
 // with `pos`: x = cat(cls, patches) + positional_embedding (model.py:280-291) folded into ln_pre (:292).
+// fold_bf16 / fold_stats (OUT_F32 only; used for ln_pre when LayerNorm is folded into the GEMMs, encoder.cu): also
+// write the bf16 copy of the output row and its (sum, sum of squares) into slot 0 of the row's `slots` partial pairs
+// (the other slots are zeroed), the format the DFD_EPI_*_LNFOLD GEMM epilogues read.
 template <int VEC, bool OUT_F32>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 const float* __restrict__ pos, int pos_period, void* __restrict__ out, int64_t rows) {
+                 const float* __restrict__ pos, int pos_period, void* __restrict__ out, int64_t rows,
+                 __nv_bfloat16* __restrict__ fold_bf16 = nullptr, float* __restrict__ fold_stats = nullptr,
+                 int slots = 0) {
   constexpr int D = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -44,6 +49,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + 1e-5f);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float o1 = 0.f, o2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
@@ -54,20 +60,37 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     y.w = (v[i].w - mean) * rstd * g.w + b.w;
     if constexpr (OUT_F32) {
       reinterpret_cast<float4*>(static_cast<float*>(out) + row * D)[i * 32 + lane] = y;
+      if (fold_bf16) {
+        reinterpret_cast<uint2*>(fold_bf16 + row * D)[i * 32 + lane] =
+            make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+        o1 += (y.x + y.y) + (y.z + y.w);
+        o2 += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+      }
     } else {
       uint2 p = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
       reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + row * D)[i * 32 + lane] = p;
+    }
+  }
+  if constexpr (OUT_F32) {
+    if (fold_stats) {
+      o1 = warp_sum(o1);
+      o2 = warp_sum(o2);
+      float2* st = reinterpret_cast<float2*>(fold_stats) + row * slots;
+      for (int sl = lane; sl < slots; sl += 32) st[sl] = (sl == 0) ? make_float2(o1, o2) : make_float2(0.f, 0.f);
     }
   }
 }
 
 template <int VEC>
 static int launch_ln(const float* x, const float* g, const float* b, const float* pos, int pos_period, void* out_bf16,
-                     float* out_f32, int64_t rows, cudaStream_t stream) {
+                     float* out_f32, int64_t rows, cudaStream_t stream, void* fold_bf16, float* fold_stats,
+                     int slots) {
   const int warps = 8;
   const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
   if (out_f32)
-    layernorm_kernel<VEC, true><<<grid, warps * 32, 0, stream>>>(x, g, b, pos, pos_period, out_f32, rows);
+    layernorm_kernel<VEC, true><<<grid, warps * 32, 0, stream>>>(x, g, b, pos, pos_period, out_f32, rows,
+                                                                static_cast<__nv_bfloat16*>(fold_bf16), fold_stats,
+                                                                slots);
   else
     layernorm_kernel<VEC, false><<<grid, warps * 32, 0, stream>>>(x, g, b, pos, pos_period, out_bf16, rows);
   DFD_CUDA_OK(cudaGetLastError());
@@ -75,24 +98,26 @@ static int launch_ln(const float* x, const float* g, const float* b, const float
 }
 
 int layernorm(const float* x, const float* gamma, const float* beta, const float* pos, int pos_period, void* out_bf16,
-              float* out_f32, int64_t rows, int D, cudaStream_t stream) {
+              float* out_f32, int64_t rows, int D, cudaStream_t stream, void* fold_bf16, float* fold_stats, int slots) {
+  DFD_CHECK_ARG((fold_bf16 == nullptr) == (fold_stats == nullptr) && (fold_bf16 == nullptr || (out_f32 && slots > 0)),
+                "layernorm: the folded outputs need out_f32, a bf16 buffer, a statistics buffer and slots > 0");
   DFD_CHECK_ARG(x && gamma && beta, "layernorm: null pointer");
   DFD_CHECK_ARG((out_bf16 != nullptr) != (out_f32 != nullptr), "layernorm: exactly one output must be given");
   DFD_CHECK_ARG(pos == nullptr || pos_period > 0, "layernorm: pos_period must be positive");
   if (rows == 0) return 0;
   DFD_CHECK_ARG(rows > 0, "layernorm: negative row count");
   switch (D) {
-    case 128: return launch_ln<1>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 256: return launch_ln<2>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 384: return launch_ln<3>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 512: return launch_ln<4>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 640: return launch_ln<5>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 768: return launch_ln<6>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 896: return launch_ln<7>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 1024: return launch_ln<8>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 1280: return launch_ln<10>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 1536: return launch_ln<12>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
-    case 2048: return launch_ln<16>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream);
+    case 128: return launch_ln<1>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 256: return launch_ln<2>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 384: return launch_ln<3>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 512: return launch_ln<4>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 640: return launch_ln<5>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 768: return launch_ln<6>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 896: return launch_ln<7>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 1024: return launch_ln<8>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 1280: return launch_ln<10>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 1536: return launch_ln<12>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
+    case 2048: return launch_ln<16>(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, stream, fold_bf16, fold_stats, slots);
     default: return fail(DFD_ERR_INVALID, "layernorm: unsupported width D=%d", D);
   }
 }
@@ -221,6 +246,42 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __
   }
 }
 
+// LayerNorm folded into a Linear (encoder.cu): one warp per output row n of W fp32 [N, K]:
+//   wf[n, k]  = bf16(gamma[k] * W[n, k])           the GEMM operand
+//   colsum[n] = sum_k float(wf[n, k])              (of the ROUNDED operand: the mean correction must cancel exactly
+//                                                   what the tensor core multiplies)
+//   bias_f[n] = bias[n] + sum_k beta[k] * W[n, k]
+__global__ void __launch_bounds__(256)
+fold_ln_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ wf, float* __restrict__ colsum,
+                      float* __restrict__ bias_f, int N, int K) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<int64_t>(n) * K + k];
+    const __nv_bfloat16 r = __float2bfloat16_rn(gamma[k] * w);
+    wf[static_cast<int64_t>(n) * K + k] = r;
+    cs += __bfloat162float(r);
+    bs = fmaf(beta[k], w, bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = bias[n] + bs;
+  }
+}
+
+int fold_ln_linear(const float* W, const float* bias, const float* gamma, const float* beta, void* wf, float* colsum,
+                   float* bias_f, int N, int K, cudaStream_t stream) {
+  fold_ln_linear_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, bias, gamma, beta, static_cast<__nv_bfloat16*>(wf), colsum,
+                                                         bias_f, N, K);
+  DFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int cast_pad_bf16(const float* src, void* dst, int64_t rows, int cols, int dst_ld, cudaStream_t stream) {
   if (rows == 0) return 0;
   cast_pad_kernel<<<592, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols, dst_ld);
@@ -234,7 +295,8 @@ extern "C" int dfd_layernorm(dfd_ctx* ctx, const float* x, const float* gamma, c
                              int pos_period, void* out_bf16, float* out_f32, int64_t rows, int D, void* stream) {
   dfd::clear_error();
   if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_layernorm: ctx is NULL");
-  return dfd::layernorm(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, D, static_cast<cudaStream_t>(stream));
+  return dfd::layernorm(x, gamma, beta, pos, pos_period, out_bf16, out_f32, rows, D, static_cast<cudaStream_t>(stream),
+                        nullptr, nullptr, 0);
 }
 
 extern "C" int dfd_patchify(dfd_ctx* ctx, const float* frames, void* out_bf16, int n_frames, int R, int patch, int Kp,

@@ -40,7 +40,11 @@ enum {
   DFD_EPI_STORE_F32 = 2,        /* out_f32  = acc + bias                     (conv1 as GEMM, :277)          */
   DFD_EPI_ADD_F32 = 3,          /* out_f32 += acc + bias  (in-place residual, out_proj/c_proj :222-223)     */
   DFD_EPI_ADD_BF16 = 4,         /* out_bf16 += acc + bias (in-place adapter residual, src/models.py:931)    */
-  DFD_EPI_STORE_BF16_GELU = 5   /* out_bf16 = gelu_erf(acc + bias)           (nn.GELU, src/models.py:893)   */
+  DFD_EPI_STORE_BF16_GELU = 5,  /* out_bf16 = gelu_erf(acc + bias)           (nn.GELU, src/models.py:893)   */
+  /* LayerNorm folded into the GEMMs around it (dfd_gemm_bf16_ln only; model.py:221-223): */
+  DFD_EPI_STORE_BF16_LNFOLD = 6,       /* out_bf16 = rstd*(acc - mu*colsum) + bias      (ln_1 + in_proj)    */
+  DFD_EPI_STORE_BF16_QGELU_LNFOLD = 7, /* out_bf16 = quickgelu(rstd*(acc - mu*colsum) + bias)  (ln_2 + c_fc) */
+  DFD_EPI_RESID_LN_F32 = 8             /* out_f32 += acc + bias, plus bf16(out) and per-row (sum, sum sq)   */
 };
 
 typedef struct dfd_ctx dfd_ctx;
@@ -69,6 +73,26 @@ const char* dfd_timing_tag_name(int tag);
  * tcgen05 / TMEM / TMA kernel. Replaces F.linear / nn.Linear / nn.Conv2d of src/clip/model.py:186,197,209,211,277. */
 int dfd_gemm_bf16(dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* out,
                   int64_t ldo, int M, int N, int K, int epilogue, void* stream);
+
+/* LayerNorm folded into the GEMMs on either side of it. With x the fp32 residual rows, LN(x) W^T =
+ * rstd * (x (gamma.W)^T - mu * colsum) + (b + W beta), colsum[n] = sum_k (gamma.W)[n,k]: the PRODUCER of x
+ * (DFD_EPI_RESID_LN_F32: x += acc + bias, the out_proj / c_proj residual update of model.py:222-223) also writes
+ * bf16(x) and, per row and per 128-column block, the partial (sum, sum of squares) of the updated values; the CONSUMER
+ * (DFD_EPI_STORE_BF16[_QGELU]_LNFOLD: in_proj / c_fc of model.py:186, 209 on A = bf16(x), W = bf16(gamma.W),
+ * bias = b + W beta) turns the partials into mu / rstd and finishes the normalisation in its epilogue. The
+ * LayerNorm pass over x disappears. N % 256 == 0, slots <= 8 (rows of at most 1024 elements); for the consumer K
+ * must be the row length the statistics were taken over. */
+typedef struct {
+  const float* stats_in; /* LNFOLD: fp32 [M, slots, 2] */
+  const float* colsum;   /* LNFOLD: fp32 [N] */
+  int slots;             /* LNFOLD: partial blocks per row (= 2 * row_length / 256 as written by RESID_LN) */
+  float* stats_out;      /* RESID_LN: fp32 [M, 2*N/256, 2] */
+  void* bf16_out;        /* RESID_LN: bf16 [M, N], row pitch ld_bf16 elements */
+  int64_t ld_bf16;
+} dfd_gemm_ln_args;
+int dfd_gemm_bf16_ln(dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                     void* out, int64_t ldo, int M, int N, int K, int epilogue, const dfd_gemm_ln_args* args,
+                     void* stream);
 
 /* Row LayerNorm, fp32 math, eps 1e-5, biased variance (src/clip/model.py:157-163).
  * x fp32 [rows, D]; pos (optional) fp32 [pos_period, D] is added to row r as pos[r % pos_period] before the

@@ -195,3 +195,62 @@ def test_project_logits(cuda_device):
     ref = 5 * l / (l.norm(dim=-1, keepdim=True) + 1e-10)
     assert (out - ref).abs().max().item() < 1e-4
     assert torch.allclose(out.norm(dim=-1), torch.full((9,), 5.0, device=cuda_device), atol=1e-4)
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 768, 768), (1000, 768, 3072), (2500, 1024, 1024)])
+def test_gemm_resid_ln(cuda_device, m, n, k):
+    """DFD_EPI_RESID_LN_F32: x += a w^T + bias with the full value in hand; also bf16(x) and, per row and 128-column
+    block, the (sum, sum of squares) of the updated values."""
+    nat = _native()
+    g = torch.Generator(device="cpu").manual_seed(m + n)
+    a = (torch.randn(m, k, generator=g)).to(cuda_device, torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(cuda_device, torch.bfloat16)
+    bias = torch.randn(n, generator=g).to(cuda_device)
+    x0 = (torch.randn(m, n, generator=g) * 3).to(cuda_device)
+    x = x0.clone()
+    xb, stats = nat.gemm_resid_ln(a, w, bias, x)
+    torch.cuda.synchronize()
+    ref = x0 + a.float() @ w.float().t() + bias
+    assert (x - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    assert torch.equal(xb.view(torch.int16), x.to(torch.bfloat16).view(torch.int16))  # bf16 copy of exactly what was stored
+    blocks = x.view(m, n // 128, 128)
+    assert tuple(stats.shape) == (m, n // 128, 2)
+    assert torch.allclose(stats[:, :, 0], blocks.sum(-1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, :, 1], (blocks * blocks).sum(-1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("m,n,quickgelu", [(300, 2304, False), (1000, 3072, True), (2000, 1024, False)])
+def test_gemm_lnfold_equals_layernorm_then_linear(cuda_device, m, n, quickgelu):
+    """LayerNorm folded into the GEMM (DFD_EPI_STORE_BF16[_QGELU]_LNFOLD) against LayerNorm -> Linear in fp32; the
+    residual stream has a per-row offset and a few large channels, as real CLIP activations do."""
+    nat = _native()
+    d = 768
+    g = torch.Generator(device="cpu").manual_seed(n)
+    x = torch.randn(m, d, generator=g) * 2 + torch.randn(m, 1, generator=g)
+    x[:, 5] += 25.0
+    x[:, 300] -= 12.0
+    gamma = 1 + 0.2 * torch.randn(d, generator=g)
+    beta = 0.3 * torch.randn(d, generator=g)
+    w = torch.randn(n, d, generator=g) * d ** -0.5
+    b = torch.randn(n, generator=g) * 0.1
+    ref = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5) @ w.t() + b
+    if quickgelu:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    blocks = x.view(m, d // 128, 128)
+    stats = torch.stack([blocks.sum(-1), (blocks * blocks).sum(-1)], dim=-1).contiguous()
+    wf = (gamma * w).to(torch.bfloat16)
+    colsum = wf.float().sum(1)
+    bf = b + w @ beta
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=cuda_device)
+    nat.gemm_lnfold(x.to(cuda_device, torch.bfloat16), stats.to(cuda_device), wf.to(cuda_device),
+                    colsum.to(cuda_device), bf.to(cuda_device), out, quickgelu=quickgelu)
+    torch.cuda.synchronize()
+    # same tolerance class as LayerNorm -> bf16 -> GEMM: compare with that pipeline's own error
+    u = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5).to(torch.bfloat16).float()
+    base = u @ w.to(torch.bfloat16).float().t() + b
+    if quickgelu:
+        base = base * torch.sigmoid(1.702 * base)
+    err_fold = (out.float().cpu() - ref).norm() / ref.norm()
+    err_base = (base - ref).norm() / ref.norm()
+    assert err_fold.item() < 1.5e-2, err_fold
+    assert err_fold.item() < 3 * err_base.item() + 4e-3, (err_fold, err_base)

@@ -219,3 +219,21 @@ def test_full_size_c2_properties(cuda_device):
     probs = full[0].softmax(-1)
     assert torch.allclose(scores[1], probs[10:40].mean(0), atol=1e-6)
     assert torch.allclose(scores.sum(-1), torch.ones(3, device=cuda_device), atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_parity_with_layernorm_folded_into_the_gemms(cuda_device):
+    """The opt-in encoder path DFD_LN_FUSE=1 (LayerNorm folded into the QKV / c_fc GEMM epilogues, residual GEMMs
+    emitting bf16(x) and row statistics) must meet the same golden-vector tolerances. The switch is read once per
+    process, so the golden-parity tests are re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DFD_LN_FUSE") == "1":
+        pytest.skip("already running with the folded path")
+    env = dict(os.environ, DFD_LN_FUSE="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_gpu.py"), "-q", "-m", "gpu",
+                          "-x", "-k", "golden or from_host or full_size"], env=env, capture_output=True, text=True,
+                         timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
