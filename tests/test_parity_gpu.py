@@ -237,3 +237,49 @@ def test_parity_with_layernorm_folded_into_the_gemms(cuda_device):
                           "-x", "-k", "golden or from_host or full_size"], env=env, capture_output=True, text=True,
                          timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
+
+
+@pytest.mark.gpu
+def test_video_level_scoring_with_the_real_detector(cuda_device):
+    """BASELINE config C3 in miniature: videos of different lengths, clips chunked per predict call, softmax per clip
+    and mean over each video's clips (inference.py:107-156) — the driver loop on the CUDA path against the oracle."""
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.inference import score_videos
+    oracle = load_oracle()
+    arch, t = "small-512x6", 3
+    det, sd = build_detector(arch, t, [0, 2, 4], cuda_device)
+    res = synthetic.vit_dims(arch)["image_size"]
+    counts = [5, 1, 9, 0, 4]
+    x, m = synthetic.make_clips(sum(counts), t, res, seed=23)
+    videos, masks, s = [], [], 0
+    for n in counts:
+        videos.append(x[s:s + n])
+        masks.append(m[s:s + n])
+        s += n
+    got = score_videos(lambda xx, mm: det.predict(xx, mm)[0][0], videos, masks, chunk_clips=4, device=cuda_device)
+    with torch.no_grad():
+        ref_logits, _ = oracle.detector_predict(sd, x, m, det.layer_indices, (2,))
+    ref = oracle.video_scores(ref_logits[0], [c for c in counts if c > 0])
+    got = got.cpu()
+    assert torch.isnan(got[3]).all()  # a video without clips is skipped (inference.py:109-111)
+    keep = [i for i, c in enumerate(counts) if c > 0]
+    assert (got[keep] - ref).abs().max().item() < 5e-3
+    assert torch.equal(got[keep].argmax(-1), ref.argmax(-1))
+
+
+@pytest.mark.gpu
+def test_long_clips_t20(cuda_device):
+    """Clips of 20 frames (the reference's T=20 configurations): S = T*P keys per clip through the streaming decoder
+    attention and the attn_mode kernels, against the oracle."""
+    from dfdclip_b200 import synthetic
+    oracle = load_oracle()
+    arch, t, b = "tiny-256x4", 20, 3
+    det, sd = build_detector(arch, t, [0, 2], cuda_device)
+    x, m = synthetic.make_clips(b, t, 32, seed=31)
+    m[2, 7:] = False
+    with torch.no_grad():
+        ref_logits, ref_feat = oracle.detector_predict(sd, x, m, [0, 2], (2,))
+    logits, feats = det.predict(x.to(cuda_device), m.to(cuda_device), with_video_features=True)
+    torch.cuda.synchronize()
+    assert (logits[0].cpu() - ref_logits[0]).abs().max().item() <= TOL_LOGIT_ABS
+    assert cosine(feats["video"].cpu(), ref_feat) >= TOL_FEATURE_COSINE
