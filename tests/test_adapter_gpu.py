@@ -184,3 +184,22 @@ def test_frozen_adapter_trains_decoder_only(cuda_device):
             p.requires_grad = True
         with pytest.raises(NotImplementedError):  # the in-place path refuses a trainable adapter under autograd
             det.adapter.apply_packed({}, [], 0, 5)
+
+
+def test_shipped_config_shape_against_oracle(cuda_device):
+    """The shape of the reference's shipped configs (configs/deepfake/*.yaml): ViT-B/16, 20 frames per clip,
+    decode_mode index with taps 6..11, `768-x-768-nln` adapter (x = 256) — the CUDA path against the oracle."""
+    from dfdclip_b200 import synthetic
+    oracle = load_oracle()
+    arch, t, b, taps = "ViT-B/16", 20, 2, [6, 7, 8, 9, 10, 11]
+    det, sd = build_adapter_detector(arch, t, "768-x-768-nln", cuda_device, decode_indices=taps)
+    x, m = synthetic.make_clips(b, t, 224, seed=41)
+    m[1, 15:] = False
+    with torch.no_grad():
+        ref_logits, ref_feat = oracle.detector_predict(sd, x, m, taps, (2,), adapter="768-x-768-nln")
+    logits, feats = det.predict(x.to(cuda_device), m.to(cuda_device), with_video_features=True)
+    torch.cuda.synchronize()
+    got, ref = logits[0].cpu().numpy(), ref_logits[0].numpy()
+    assert np.abs(got - ref).max() <= TOL_LOGIT_ABS, np.abs(got - ref).max()
+    check_labels(got, ref)
+    assert cosine(feats["video"].cpu(), ref_feat) >= TOL_FEATURE_COSINE
