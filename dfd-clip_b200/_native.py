@@ -263,6 +263,8 @@ def layernorm(x, gamma, beta, pos=None, out_dtype=torch.bfloat16, out=None):
     if out is None:
         out = torch.empty((rows, d), dtype=out_dtype, device=x.device)
     bf = out.dtype == torch.bfloat16
+    if rows == 0:
+        return out
     check(load_library().dfd_layernorm(ctx(x.device), ptr(x), ptr(gamma), ptr(beta), ptr(pos),
                                        0 if pos is None else pos.shape[0], ptr(out) if bf else None,
                                        None if bf else ptr(out), rows, d, stream_ptr(x.device)))
@@ -393,6 +395,8 @@ def adapter_apply(kind, kv, rows, ld, width, inner, w_down, w_mid, w_up, ln_weig
     lib = load_library()
     dev = kv.device
     assert kv.dtype == torch.bfloat16
+    if rows == 0:
+        return workspace
     nbytes = lib.dfd_adapter_workspace_bytes(kind, width, inner, rows)
     if workspace is None or workspace.numel() < nbytes or workspace.device != dev:
         workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)

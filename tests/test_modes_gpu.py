@@ -160,3 +160,26 @@ def test_decoder_attention_modes_unit_vitb_shapes(cuda_device, mode):
                                    tuple(mode.split("+")), t).reshape(b, h * 64)
     assert torch.isfinite(got).all()
     assert (got.cpu() - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_empty_batch_with_adapter_and_global_prediction(cuda_device):
+    """An empty batch flows through the adapter, the per-layer ln_post and the stacked projection without touching
+    a kernel (the reference returns empty tensors too)."""
+    from dfdclip_b200.config import CN
+    from dfdclip_b200.models import Detector
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:tiny-256x4"
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    cfg.op_mode.global_prediction = 1
+    cfg.op_mode.aug_query = 1
+    cfg.adapter.type = "normal"
+    cfg.adapter.frozen = 0
+    cfg.adapter.struct = CN({"type": "768-x-768-z0", "x": 256})
+    det = Detector(cfg, 4, None).to(cuda_device).eval()
+    x = torch.zeros(0, 4, 3, 32, 32, device=cuda_device)
+    m = torch.zeros(0, 4, dtype=torch.bool, device=cuda_device)
+    logits, feats = det.predict(x, m, with_video_features=True, with_adapt_features=True)
+    assert tuple(logits[0].shape) == (0, 2)
+    assert tuple(feats["video"].shape) == (0, 2, 256)
+    assert len(feats["adapt"]) == 2 and feats["adapt"][0]["k"].shape[0] == 0
