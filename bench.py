@@ -41,8 +41,9 @@ def flops_per_clip(dims, frames, taps, executed=True):
     full = qkv + attn + out + mlp
     if executed:
         last = max(taps)
-        per_frame = patch + last * full + qkv
-        gemm = patch + last * (qkv + out + mlp) + qkv
+        kv_only = qkv * 2 // 3  # the last tapped layer computes K and V only
+        per_frame = patch + last * full + kv_only
+        gemm = patch + last * (qkv + out + mlp) + kv_only
     else:
         per_frame = patch + layers * full
         gemm = patch + layers * (qkv + out + mlp)

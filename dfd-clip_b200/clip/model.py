@@ -183,7 +183,8 @@ class VisionTransformer(nn.Module):
         Run the encoder on frames x[N,3,R,R] (fp32, cuda). Returns ``(qkv, outs)``: ``qkv[l]`` is the packed
         bf16 ``[N*L, 3D]`` buffer of layer l for every l in ``keep_layers`` (default: all layers), ``outs[l]`` the
         fp32 residual stream after layer l when ``need_out``. Layers after the last kept one are not executed, and
-        the last kept layer stops after its QKV projection unless ``need_out`` (dead-work skipping)."""
+        the last kept layer stops after its K/V projection unless ``need_out`` or ``last_qkv_only=False`` (dead-work
+        skipping): the Q block of that layer's buffer is then left unwritten."""
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
             raise ValueError("expected frames of shape [N,3,%d,%d], got %s" %
                              (self.input_resolution, self.input_resolution, tuple(x.shape)))

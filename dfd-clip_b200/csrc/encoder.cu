@@ -252,10 +252,18 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
   for (int l = 0; l < num_run_layers && fuse; ++l) {
     const size_t lb = pl.layer0 + pl.layer_stride * l;
     void* qkv = (qkv_out && qkv_out[l]) ? qkv_out[l] : static_cast<void*>(ws + wl.qkv);
+    if (l == num_run_layers - 1 && last_qkv_only) {
+      // only K and V of this layer are consumed (tap): skip the Q third of the projection
+      fold_in.colsum = f32p(lb + pl.c_in) + D;
+      DFD_TIMED(DFD_TAG_GEMM_QKV,
+                gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_in + static_cast<size_t>(D) * D * 2, D, f32p(lb + pl.bf_in) + D,
+                             static_cast<uint8_t*>(qkv) + static_cast<size_t>(D) * 2, 3 * D, M, 2 * D, D,
+                             DFD_EPI_STORE_BF16_LNFOLD, &fold_in, stream));
+      break;
+    }
     fold_in.colsum = f32p(lb + pl.c_in);
     DFD_TIMED(DFD_TAG_GEMM_QKV, gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_in, D, f32p(lb + pl.bf_in), qkv, 3 * D, M,
                                              3 * D, D, DFD_EPI_STORE_BF16_LNFOLD, &fold_in, stream));
-    if (l == num_run_layers - 1 && last_qkv_only) break;
     DFD_TIMED(DFD_TAG_MHA, mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
     DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16_ln(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
                                              DFD_EPI_RESID_LN_F32, &resid, stream));
@@ -275,9 +283,16 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
     // a = attn(ln_1(x))
     DFD_TIMED(DFD_TAG_LAYERNORM,
               layernorm(x, f32p(lb + pl.ln1_w), f32p(lb + pl.ln1_b), nullptr, 0, u, nullptr, M, D, stream));
+    if (l == num_run_layers - 1 && last_qkv_only) {
+      // only K and V of this layer are consumed (tap): skip the Q third of the projection
+      DFD_TIMED(DFD_TAG_GEMM_QKV,
+                gemm_bf16(ctx, u, D, pk + lb + pl.w_in + static_cast<size_t>(D) * D * 2, D, f32p(lb + pl.b_in) + D,
+                          static_cast<uint8_t*>(qkv) + static_cast<size_t>(D) * 2, 3 * D, M, 2 * D, D,
+                          DFD_EPI_STORE_BF16, stream));
+      break;
+    }
     DFD_TIMED(DFD_TAG_GEMM_QKV, gemm_bf16(ctx, u, D, pk + lb + pl.w_in, D, f32p(lb + pl.b_in), qkv, 3 * D, M, 3 * D, D,
                                           DFD_EPI_STORE_BF16, stream));
-    if (l == num_run_layers - 1 && last_qkv_only) break;
     DFD_TIMED(DFD_TAG_MHA, mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
     // x = x + out_proj(mix)
     DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,

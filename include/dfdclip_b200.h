@@ -158,7 +158,8 @@ int dfd_encoder_pack_weights(dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd_v
                              void* stream);
 
 /* frames fp32 [n_frames,3,R,R]. Runs layers [0, num_run_layers). If last_qkv_only != 0 the last of those
- * layers stops after its QKV projection (its attention/MLP output is not needed: SURVEY note D1).
+ * layers stops after its K/V projection (its attention/MLP output is not needed: SURVEY note D1; the Q block of that
+ * layer's buffer is NOT written).
  * qkv_out: HOST array [layers] of bf16 [n_frames*L, 3D] device buffers (NULL entry: QKV of that layer is kept
  * only in scratch). x_out: NULL or HOST array [layers] of fp32 [n_frames*L, D] device buffers receiving the
  * residual stream after each layer (`with_out`, model.py:242). */
