@@ -283,3 +283,34 @@ def test_long_clips_t20(cuda_device):
     torch.cuda.synchronize()
     assert (logits[0].cpu() - ref_logits[0]).abs().max().item() <= TOL_LOGIT_ABS
     assert cosine(feats["video"].cpu(), ref_feat) >= TOL_FEATURE_COSINE
+
+
+@pytest.mark.gpu
+def test_predict_is_cuda_graph_capturable(cuda_device):
+    """Every launch of the path goes to the caller's stream and nothing synchronises the device, so a whole
+    Detector.predict can be captured in a CUDA graph; replays are bit-identical to the eager call and follow the
+    contents of the captured input buffers."""
+    from dfdclip_b200 import synthetic
+    arch, t, b = "small-512x6", 3, 6
+    det, _ = build_detector(arch, t, [0, 2, 4], cuda_device)
+    res = synthetic.vit_dims(arch)["image_size"]
+    x, m = synthetic.make_clips(b, t, res, seed=3)
+    x2, _ = synthetic.make_clips(b, t, res, seed=4)
+    xs, m = x.to(cuda_device).clone(), m.to(cuda_device)
+    ref1 = det.predict(xs, m)[0][0].clone()          # also warms up (weight packing, function attributes)
+    ref2 = det.predict(x2.to(cuda_device), m)[0][0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        det.predict(xs, m)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = det.predict(xs, m)[0][0]
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref1)
+    xs.copy_(x2.to(cuda_device))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref2)
