@@ -359,6 +359,25 @@ def run_b200(args, rank, world, local_rank):
         "whole_step_frac": total_flops * clips / (elapsed_ms / args.steps * 1e-3) / 1e12 / peaks["tflops"],
         "by_kernel_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(kernel_ms.items())},
     }
+    # HBM-bound sub-kernels: algorithmic bytes / measured duration against the measured copy bandwidth
+    seq = (dims["image_size"] // dims["patch_size"]) ** 2 + 1
+    m_rows = clips * frames * seq
+    hbm = {}
+    if "layernorm" in kernel_ms:
+        ln_ms, ln_n = kernel_ms["layernorm"]
+        ln_bytes = m_rows * dims["width"] * (4 + 2)          # fp32 row in, bf16 row out
+        hbm["layernorm"] = {"bytes_per_launch": ln_bytes, "launches_per_step": ln_n / args.steps,
+                            "achieved_gbs": ln_bytes * ln_n / (ln_ms * 1e-3) / 1e9}
+    if "dec_attn" in kernel_ms:
+        da_ms, da_n = kernel_ms["dec_attn"]
+        da_bytes = 2 * clips * frames * (seq - 1) * dims["width"] * 2   # K and V of every patch token, bf16, once
+        hbm["dec_attn"] = {"bytes_per_launch": da_bytes, "launches_per_step": da_n / args.steps,
+                           "achieved_gbs": da_bytes * da_n / (da_ms * 1e-3) / 1e9,
+                           "note": "duration includes the cross-unit combine kernel"}
+    for v in hbm.values():
+        v["peak_gbs"] = peaks["hbm_gbs"]
+        v["frac"] = v["achieved_gbs"] / peaks["hbm_gbs"] if peaks["hbm_gbs"] else None
+    roofline["hbm_kernels"] = hbm
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, times, cores = cpu_reference_clips_per_sec(args.arch, frames, args.ref_clips, repeats=4)

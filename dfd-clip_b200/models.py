@@ -31,7 +31,16 @@ def auc_roc(weight=None, label_smoothing=0.0, *args, **kargs):
     return driver
 
 
-_LOSSES = {"auc_roc": auc_roc}
+def kl_div(*args, **kargs):
+    """KL divergence to a target distribution per sample (reference :27-30)."""
+
+    def driver(logits, y):
+        return torch.nn.functional.kl_div(torch.nn.functional.log_softmax(logits, dim=1), y, reduction="none")
+
+    return driver
+
+
+_LOSSES = {"auc_roc": auc_roc, "kl_div": kl_div}
 
 
 def disable_gradients(module: nn.Module):
@@ -550,8 +559,12 @@ class Detector(nn.Module):
         if config.adapter.type not in ("none", "normal", "pretrain"):
             raise NotImplementedError("adapter.type=%r" % (config.adapter.type,))
         for key in config.train_mode:
-            if key != "patch_mask":  # "temporal" (ranking loss) and "compression" (adapter losses): trainer-side extras
+            # "compression" / "nerf_raw" cannot run in the reference either: Decoder.forward flattens the adapted
+            # taps in place (:332-334) before Detector.forward unpacks their five dimensions (:604) -> ValueError
+            if key not in ("patch_mask", "temporal"):
                 raise NotImplementedError("train_mode.%s is not implemented by the B200 path" % (key,))
+        if "temporal" in config.train_mode and config.train_mode.temporal not in ("ranking", "triplet"):
+            raise NotImplementedError("train_mode.temporal=%r" % (config.train_mode.temporal,))
         if "ema_frame" in config.op_mode and config.op_mode.ema_frame and \
                 "temporal_position" in config.op_mode and config.op_mode.temporal_position:
             # the reference broadcasts the single EMA frame against the [T,1,H,dh] embedding and then fails on the
@@ -594,6 +607,9 @@ class Detector(nn.Module):
                     self.adapter = disable_gradients(self.adapter)
         self.transform = self._transform(self.encoder.input_resolution)
         self.encoder.input_mean, self.encoder.input_std = self._MEAN, self._STD
+        if "temporal" in self.train_mode and self.train_mode.temporal == "ranking":  # reference :488-492
+            self.ranking_transform_param = nn.Parameter(
+                (self.encoder.width ** -0.5) * torch.randn(self.encoder.width, 1), requires_grad=True)
         if "patch_mask" in self.train_mode and self.train_mode.patch_mask.type == "guide":
             import pickle
             with open(self.train_mode.patch_mask.path, "rb") as f:  # reference :493-495
@@ -644,7 +660,8 @@ class Detector(nn.Module):
         if with_video_features:
             features["video"] = video_features
         if with_adapt_features:
-            features["adapt"] = [{n: kv[n].float() for n in ("k", "v")} for kv in kvs]
+            # the adapted taps as the decoder received them (autograd tensors when the adapter is being trained)
+            features["adapt"] = kvs if adapter_autograd else [{n: kv[n].float() for n in ("k", "v")} for kv in kvs]
         return task_logits, features
 
     def _mask_patches(self, kvs):
@@ -681,14 +698,53 @@ class Detector(nn.Module):
                 raise NotImplementedError("op_mode.ema_frame averages normalised float frames: pass fp32 clips")
             x = _native.ema_frames(x, float(self.op_mode.ema_frame))
             m = m[:, 0].unsqueeze(1)
+        b = x.shape[0]
         task_logits, features = self.predict(x, m, with_video_features=True, train=train)
+        video_features = features["video"]
         task_losses = [
             loss_fn(logits, labels) if single_task is None or i == single_task else 0
             for i, loss_fn, logits, labels in zip(range(len(self.losses)), self.losses, task_logits, y)
         ]
         if not train:
             return task_losses, task_logits
-        return task_losses, task_logits, {}
+        return task_losses, task_logits, self._auxiliary_losses(video_features, speed, b)
+
+    def _auxiliary_losses(self, video_features, speed, b):
+        """The trainer's extra term that the reference can execute (reference :676-736): ``train_mode.temporal``, a
+        speed ranking / triplet loss in plain torch on the [B, D] video features."""
+        import random
+        from itertools import combinations
+        from math import comb as n_choose
+        device = video_features.device
+        other_losses = {}
+        if "temporal" in self.train_mode:
+            speed_rank_index = torch.argsort(speed, descending=True).tolist()
+            speed_loss = torch.tensor(0.0, device=device)
+            if self.train_mode.temporal == "ranking":
+                rank_logits = (video_features @ self.ranking_transform_param).squeeze()
+                rank_losses = []
+                for rank in range(0, b - 1):
+                    input1 = rank_logits[speed_rank_index[rank]].repeat(b - 1 - rank)
+                    input2 = rank_logits[speed_rank_index[rank + 1:], ...]
+                    target = torch.ones(b - 1 - rank, device=device)
+                    rank_losses.append(torch.nn.functional.margin_ranking_loss(input1, input2, target,
+                                                                               reduction="none"))
+                other_losses["speed/rank"] = 0.05 * torch.cat(rank_losses).mean()
+            else:  # "triplet"
+                margin_rounds = min(n_choose(b, 3), 10)
+                indices = list(range(b))
+                random.shuffle(indices)
+                triples = iter(combinations(indices, 3))
+                for _ in range(margin_rounds):
+                    b_index = sorted(next(triples), key=lambda _i: speed_rank_index.index(_i))
+                    speed_loss = speed_loss + torch.nn.functional.triplet_margin_loss(
+                        anchor=video_features[b_index[0]], positive=video_features[b_index[1]],
+                        negative=video_features[b_index[2]], margin=torch.abs(speed[b_index[2]] - speed[b_index[1]]))
+                    speed_loss = speed_loss + torch.nn.functional.triplet_margin_loss(
+                        anchor=video_features[b_index[2]], positive=video_features[b_index[1]],
+                        negative=video_features[b_index[0]], margin=torch.abs(speed[b_index[1]] - speed[b_index[0]]))
+                other_losses["speed/triplet"] = 0.01 * speed_loss / (margin_rounds * 2)
+        return other_losses
 
     def configure_optimizers(self, lr):
         params = [i for i in self.parameters() if i.requires_grad]

@@ -192,7 +192,7 @@ def adapter_state_dict(arch, n_taps, struct_type, inner=256, seed=0):
 
 
 def detector_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, adapter=None, adapter_inner=256,
-                        **decoder_options):
+                        ranking=False, **decoder_options):
     """Full ``Detector.state_dict()`` (encoder.* + decoder.* [+ adapter.*]), the on-disk format of ``*_weights.pt``
     (written at main.py:119-129, loaded strictly at inference.py:99). ``adapter`` = an
     ``adapter.struct.type`` string adds the CompInvAdapter parameters."""
@@ -200,6 +200,9 @@ def detector_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, adap
     sd = OrderedDict(("encoder." + k, v) for k, v in visual.items())
     for k, v in decoder_state_dict(arch, num_frames, out_dims, taps, seed, visual, **decoder_options).items():
         sd["decoder." + k] = v
+    if ranking:  # train_mode.temporal == "ranking" (src/models.py:488-492)
+        w = vit_dims(arch)["width"]
+        sd["ranking_transform_param"] = _randn(seed, "ranking_transform_param", (w, 1), w ** -0.5)
     if adapter is not None:
         n_taps = len(layer_indices(arch) if taps is None else list(taps))
         for k, v in adapter_state_dict(arch, n_taps, adapter, adapter_inner, seed).items():

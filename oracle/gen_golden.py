@@ -54,6 +54,9 @@ CASES = {
     "tiny_attn_frame": ("tiny-256x4", 4, 3, True, None, {"attn_mode": "frame"}),
     "tiny_attn_tf": ("tiny-256x4", 4, 3, True, None, {"attn_mode": "temporal+frame"}),
     "small_attn_temporal": ("small-512x6", 3, 2, False, None, {"attn_mode": "temporal"}),
+    # trainer-side auxiliary losses of Detector.forward(train=True) (src/models.py:598-738)
+    "small_tm_ranking": ("small-512x6", 3, 4, False, None, None, None, {"temporal": "ranking"}),
+    "small_tm_triplet": ("small-512x6", 3, 4, False, None, None, None, {"temporal": "triplet"}),
     "small_pm_batch": ("small-512x6", 3, 2, False, None, None, {"type": "batch", "ratio": 0.5}),
     "small_pm_sample": ("small-512x6", 3, 2, False, None, None, {"type": "sample", "ratio": 0.5}),
     "tiny_pm_adapter": ("tiny-256x4", 4, 3, True, "768-x-768-z0", None, {"type": "batch", "ratio": 0.5}),
@@ -113,7 +116,7 @@ def sample_indices(numel, seed):
     return torch.randint(0, numel, (min(N_SAMPLES, numel),), generator=g)
 
 
-def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, patch_mask=None):
+def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, patch_mask=None, train_mode=None):
     from src.models import Detector  # the reference's own class
 
     dims = synthetic.vit_dims(arch)
@@ -130,6 +133,8 @@ def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, pa
         cfg.op_mode[key] = val
     if patch_mask is not None:
         cfg.train_mode["patch_mask"] = CfgNode(dict(patch_mask))
+    for key, val in (train_mode or {}).items():
+        cfg.train_mode[key] = val
     if adapter is not None:
         cfg.adapter.type = "normal"
         cfg.adapter.frozen = 0
@@ -142,7 +147,8 @@ def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, pa
     sd = synthetic.detector_state_dict(arch, num_frames, out_dims=(2,), taps=det.layer_indices, seed=0,
                                        adapter=adapter, adapter_inner=256, aug_query=bool(op.get("aug_query")),
                                        global_prediction=bool(op.get("global_prediction")),
-                                       temporal_position=bool(op.get("temporal_position", 1)))
+                                       temporal_position=bool(op.get("temporal_position", 1)),
+                                       ranking=(train_mode or {}).get("temporal") == "ranking")
     # the encoder built by the reference's clip.load/build_model must equal the synthetic fp32 values exactly
     # (they are fp16-representable where build_model rounds)
     for k, v in det.encoder.state_dict().items():
@@ -174,6 +180,20 @@ def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, pa
             extra["patch_indices"] = np.stack(drawn)
             extra["patch_mask_type"] = np.array(patch_mask["type"])
             extra["patch_mask_ratio"] = np.array(patch_mask["ratio"])
+        elif train_mode:
+            # Detector.forward(train=True): task losses + the auxiliary losses; the module stays in eval mode
+            # (dropout is 0) and the sample pairs alternate raw / c23 like the compression sampler produces them
+            import random
+            comp = ["raw" if i % 2 == 0 else "c23" for i in range(batch)]
+            speed = torch.linspace(0.7, 1.3, batch)[torch.randperm(batch, generator=torch.Generator().manual_seed(5))]
+            random.seed(11)
+            losses, logits, other = det(x, [labels], m, comp=comp, speed=speed, train=True, single_task=0)
+            logits2, feats = logits, {"video": np.zeros((0,), dtype=np.float32)}
+            extra["speed"] = speed.numpy()
+            extra["comp_raw_first"] = np.array(True)
+            extra["train_mode"] = np.array(repr(sorted(train_mode.items())))
+            for key, val in other.items():
+                extra["other_" + key.replace("/", "_")] = np.array(float(val))
         elif op.get("ema_frame"):
             # ema_frame acts in Detector.forward, not in predict (:572-578)
             losses, logits = det(x, [labels], m, single_task=0)
@@ -194,6 +214,7 @@ def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, pa
         out["op_mode"] = np.array(repr(sorted(op.items())))
     if adapter is not None:
         out["adapter"] = np.array(adapter)
+    if adapter is not None and not train_mode:
         # adapted taps as the decoder received them: predict's kvs after the adapter AND after Decoder.forward's
         # in-place list edits (positional embedding added, (t, p) flattened — src/models.py:326-334)
         for i, kv in enumerate(feats["adapt"]):
@@ -209,7 +230,7 @@ def run_case(name, arch, num_frames, batch, full, adapter=None, op_mode=None, pa
                     out["idx_adapt_%s_%d" % (key, i)] = idx.numpy()
                     out["val_adapt_%s_%d" % (key, i)] = t.flatten()[idx].detach().numpy()
     for i, a in enumerate(taps):
-        if adapter is not None or op_mode or patch_mask:
+        if adapter is not None or op_mode or patch_mask or train_mode:
             break  # the raw taps are pinned by the default-mode cases
         for key in ("q", "k", "v", "out"):
             t = a[key].contiguous().float()

@@ -119,7 +119,7 @@ def test_index_decode_mode_and_unsupported_knobs():
                    lambda c: (c.adapter.__setitem__("type", "normal"),
                               c.adapter.__setitem__("struct", CN({"type": "768-x-768-z0", "x": 100}))),
                    lambda c: c.__setitem__("foundation", "dinov2"),
-                   lambda c: c.train_mode.__setitem__("temporal", "ranking")):
+                   lambda c: c.train_mode.__setitem__("compression", "sync")):
         cfg = Detector.get_default_config()
         cfg.architecture = "synthetic:tiny-256x4"
         cfg.out_dim = [2]

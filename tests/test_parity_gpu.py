@@ -142,7 +142,7 @@ def test_unsupported_configs_raise(cuda_device):
     cfg.architecture = "synthetic:tiny-256x4"
     cfg.out_dim = [2]
     cfg.losses = ["auc_roc"]
-    cfg.train_mode.temporal = "ranking"
+    cfg.train_mode.compression = "sync"
     with pytest.raises(NotImplementedError):
         Detector(cfg, 4, None)
     cfg = Detector.get_default_config()

@@ -192,3 +192,52 @@ def test_training_step_with_trainable_adapter(cuda_device, struct):
     det.eval()
     a, _ = det.predict(x.to(cuda_device), m.to(cuda_device))
     assert (a[0] - logits[0].detach()).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("mode,key", [("ranking", "speed/rank"), ("triplet", "speed/triplet")])
+def test_temporal_train_mode_matches_reference_golden(cuda_device, mode, key):
+    """train_mode.temporal (src/models.py:676-736): the speed ranking / triplet loss of Detector.forward(train=True)
+    on the video features, against the unmodified reference (oracle/gen_golden.py, cases small_tm_*)."""
+    import random
+    import numpy as np
+    from helpers import load_golden
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.models import Detector
+    g = load_golden("small_tm_" + mode)
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:" + g["arch"]
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    cfg.train_mode["temporal"] = mode
+    det = Detector(cfg, g["num_frames"], None)
+    sd = synthetic.detector_state_dict(g["arch"], g["num_frames"], out_dims=(2,), taps=det.layer_indices, seed=0,
+                                       ranking=(mode == "ranking"))
+    det.load_state_dict(sd, strict=True)
+    det = det.to(cuda_device).eval()
+    x, m = synthetic.make_clips(g["batch"], g["num_frames"], synthetic.vit_dims(g["arch"])["image_size"], seed=7)
+    y = torch.from_numpy(g["labels"]).to(cuda_device)
+    speed = torch.from_numpy(g["speed"]).to(cuda_device)
+    comp = ["raw" if i % 2 == 0 else "c23" for i in range(g["batch"])]
+    random.seed(11)
+    with torch.enable_grad():
+        losses, logits, other = det(x.to(cuda_device), [y], m.to(cuda_device), comp=comp, speed=speed, train=True,
+                                    single_task=0)
+        (losses[0].mean() + other[key]).backward()
+    ref = float(g["other_" + key.replace("/", "_")])
+    assert list(other) == [key]
+    assert abs(other[key].item() - ref) <= 0.03 * abs(ref) + 1e-4, (other[key].item(), ref)
+    assert np.abs(losses[0].detach().cpu().numpy() - g["losses"]).max() <= 4e-2
+    if mode == "ranking":
+        assert det.ranking_transform_param.grad is not None
+    assert det.decoder.class_embedding.grad is not None
+
+
+def test_train_modes_the_reference_cannot_run_raise():
+    from dfdclip_b200.models import Detector
+    for key, val in (("compression", "sync"), ("nerf_raw", 0.5), ("temporal", "order")):
+        cfg = Detector.get_default_config()
+        cfg.architecture = "synthetic:tiny-256x4"
+        cfg.out_dim = [2]
+        cfg.train_mode[key] = val
+        with pytest.raises(NotImplementedError):
+            Detector(cfg, 4, None)
