@@ -139,6 +139,53 @@ def video_mean_probs(clip_logits, clip_counts):
     return sums / counts.clamp_min(1).unsqueeze(1).to(probs.dtype)
 
 
+def score_videos_batched(detector, videos, masks, batch_clips=64, group=None):
+    """The same result as ``score_videos`` for host-resident videos, computed the way the hardware likes it: the
+    clips of ALL of this rank's videos are packed into batches of ``batch_clips`` (video boundaries do not matter:
+    clips are independent) and pushed through ``HostClipPipeline`` (H2D double-buffered under the encoder, decoder once
+    per batch, one D2H of the logits); the per-video mean of clip probabilities is a segment mean at the end and ONE
+    all_gather assembles the ranks' scores. The reference scores one video at a time in chunks of 16 clips with a
+    blocking copy in each direction per chunk (inference.py:107-156).
+
+    ``videos[i]``: host tensor [n_i, T, 3, R, R] (fp32 normalised or uint8), ``masks[i]``: [n_i, T].
+    Returns per-video mean probabilities [len(videos), O] on the detector's device, identical on every rank."""
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized() and (dist.get_world_size(group) > 1)
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    counts = [int(v.shape[0]) for v in videos]
+    shards = shard_videos(counts, world)
+    mine = [i for i in shards[rank] if counts[i] > 0]
+    dev = next(detector.decoder.parameters()).device
+    out_dim = detector.out_dim[0]
+    result = torch.full((len(videos), out_dim), float("nan"), device=dev)
+    if mine:
+        x_host = torch.cat([videos[i] for i in mine])
+        m_host = torch.cat([masks[i] for i in mine])
+        if not x_host.is_pinned():
+            x_host, m_host = x_host.pin_memory(), m_host.pin_memory()
+        pipe = HostClipPipeline(detector)
+        pipe.MAX_BATCH = int(batch_clips)
+        logits = pipe(x_host, m_host).to(dev)
+        rows = video_mean_probs(logits, [counts[i] for i in mine])
+    else:
+        rows = torch.empty((0, out_dim), device=dev)
+    if not distributed:
+        if mine:
+            result[torch.as_tensor(mine, dtype=torch.long, device=dev)] = rows
+        return result
+    kept = [[i for i in s if counts[i] > 0] for s in shards]
+    width = max(1, max(len(k) for k in kept))
+    padded = torch.full((width, out_dim), float("nan"), device=dev)
+    padded[:rows.shape[0]] = rows
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)  # the single collective of the path
+    for r, idx in enumerate(kept):
+        if idx:
+            result[torch.as_tensor(idx, dtype=torch.long, device=dev)] = gathered[r][:len(idx)]
+    return result
+
+
 def score_videos(predict_fn, videos, masks, chunk_clips=16, group=None, device=None):
     """Score a list of videos. ``videos[i]``: tensor [n_i, T, 3, R, R] of that video's clips, ``masks[i]``: [n_i, T].
     ``predict_fn(x, m) -> logits [n, O]`` (e.g. ``lambda x, m: det.predict(x, m)[0][0]``).

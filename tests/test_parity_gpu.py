@@ -260,6 +260,9 @@ def test_video_level_scoring_with_the_real_detector(cuda_device):
     with torch.no_grad():
         ref_logits, _ = oracle.detector_predict(sd, x, m, det.layer_indices, (2,))
     ref = oracle.video_scores(ref_logits[0], [c for c in counts if c > 0])
+    from dfdclip_b200.inference import score_videos_batched
+    batched = score_videos_batched(det, videos, masks, batch_clips=7)  # batches cut across video boundaries
+    assert torch.equal(torch.nan_to_num(batched), torch.nan_to_num(got))
     got = got.cpu()
     assert torch.isnan(got[3]).all()  # a video without clips is skipped (inference.py:109-111)
     keep = [i for i, c in enumerate(counts) if c > 0]
