@@ -40,6 +40,7 @@ class HostClipPipeline:
     def __init__(self, detector, chunk_clips=32):
         self.det = detector
         self.chunk = int(chunk_clips)
+        self.chunk_u8 = (16, 48, 64)  # first, second, following chunk sizes for uint8 clips
         self.dev = next(detector.decoder.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("HostClipPipeline needs the detector on a CUDA device")
@@ -66,7 +67,11 @@ class HostClipPipeline:
     def _run_batch(self, x_host, m_host, out_host):
         n, t = x_host.shape[:2]
         det, dev, main = self.det, self.dev, torch.cuda.current_stream(self.dev)
-        sizes = chunk_schedule(n, self.chunk)
+        if x_host.dtype == torch.uint8:
+            # 1 byte per pixel: the copies are four times shorter, so fewer and larger chunks win
+            sizes = chunk_schedule(n, self.chunk_u8[2], first=self.chunk_u8[0], second=self.chunk_u8[1])
+        else:
+            sizes = chunk_schedule(n, self.chunk)
         bufs = self._buffers(x_host, max(sizes))
         taps = self._tap_buffers(n * t)
         m_dev = m_host.to(dev, non_blocking=True)
