@@ -2,11 +2,13 @@
 ``Decoder`` (:272-361) with the same constructor, methods, attributes and ``state_dict()`` key schema
 (SURVEY App. B.3), computing on the B200 through libdfdclip_b200.so.
 
-Supported configuration = the reference's defaults (``Detector.get_default_config`` :406-431): CLIP foundation,
-stride or index taps, ``op_mode.temporal_position`` on or off, empty ``train_mode`` — plus the ``CompInvAdapter``
-(:783-940) of the shipped configs in inference (and frozen in training). Every other knob raises
-``NotImplementedError`` instead of silently diverging. There is no CPU / PyTorch fallback for the encoder
-or the decoder attention.
+Supported: the CLIP foundation with stride or index taps; every ``op_mode`` switch of the reference
+(``temporal_position``, ``aug_query``, ``global_prediction``, ``ema_frame``, ``attn_mode``); ``train_mode.patch_mask``
+and ``train_mode.temporal``; dropout; the ``CompInvAdapter`` (:783-940) with every struct but ``768-bn`` — natively
+in place on the taps in inference or when frozen, under autograd (with native dK/dV from the decoder attention) when
+trained. What is not implemented (``foundation: dinov2``, ``768-bn``, and ``train_mode.compression`` / ``nerf_raw``,
+which the reference itself cannot execute) raises ``NotImplementedError`` instead of silently diverging. There is no
+CPU / PyTorch fallback for the encoder, the adapter's inference path or the decoder attention.
 """
 import ctypes
 from collections import OrderedDict
