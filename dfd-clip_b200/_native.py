@@ -27,7 +27,7 @@ EXPORTS = (
     "dfd_decoder_attention_workspace_bytes", "dfd_decoder_attention_train", "dfd_decoder_attention_backward",
     "dfd_adapter_workspace_bytes", "dfd_adapter_apply", "dfd_ema_frames",
     "dfd_decoder_attention_modes_workspace_bytes", "dfd_decoder_attention_modes",
-    "dfd_patchify_u8", "dfd_encoder_forward_u8", "dfd_gemm_bf16_ln",
+    "dfd_patchify_u8", "dfd_encoder_forward_u8", "dfd_gemm_bf16_ln", "dfd_predict_forward",
 )
 
 
@@ -125,6 +125,11 @@ def load_library():
         lib.dfd_decoder_forward.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
                                             ctypes.POINTER(KvTaps), c_void_p, c_int, c_int, c_int, c_void_p,
                                             c_void_p, c_void_p, c_size_t, c_void_p]
+        lib.dfd_predict_forward.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p, c_int,
+                                            ctypes.POINTER(c_float), c_int, c_int, c_int, _PP, c_void_p, c_size_t,
+                                            c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
+                                            ctypes.POINTER(KvTaps), ctypes.POINTER(c_int), c_void_p, c_int, c_int,
+                                            c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]
         lib.dfd_project_logits.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                            c_void_p]
         lib.dfd_decoder_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,

@@ -185,6 +185,26 @@ class VisionTransformer(nn.Module):
         fp32 residual stream after layer l when ``need_out``. Layers after the last kept one are not executed, and
         the last kept layer stops after its K/V projection unless ``need_out`` or ``last_qkv_only=False`` (dead-work
         skipping): the Q block of that layer's buffer is then left unwritten."""
+        plan = self._encode_plan(x, keep_layers, need_out, last_qkv_only, qkv_into, frame_offset)
+        if plan["n"] == 0:
+            return plan["qkv"], plan["outs"]
+        lib, dev = _native.load_library(), plan["dev"]
+        with torch.cuda.device(dev):
+            if plan["x"].dtype == torch.uint8:
+                _native.check(lib.dfd_encoder_forward_u8(
+                    _native.ctx(dev), ctypes.byref(plan["dims"]), _native.ptr(plan["packed"]), _native.ptr(plan["x"]),
+                    plan["mean_std"], plan["n"], plan["run_layers"], plan["qkv_only"], plan["qkv_pp"], plan["out_pp"],
+                    _native.ptr(plan["ws"]), plan["ws_bytes"], _native.stream_ptr(dev)))
+            else:
+                _native.check(lib.dfd_encoder_forward(
+                    _native.ctx(dev), ctypes.byref(plan["dims"]), _native.ptr(plan["packed"]), _native.ptr(plan["x"]),
+                    plan["n"], plan["run_layers"], plan["qkv_only"], plan["qkv_pp"], plan["out_pp"],
+                    _native.ptr(plan["ws"]), plan["ws_bytes"], _native.stream_ptr(dev)))
+        return plan["qkv"], plan["outs"]
+
+    def _encode_plan(self, x, keep_layers=None, need_out=False, last_qkv_only=None, qkv_into=None, frame_offset=0):
+        """Argument checking, output / workspace buffers and pointer arrays of one encoder pass (everything ``encode``
+        does short of the launch; ``Detector.predict`` hands the same plan to ``dfd_predict_forward``)."""
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
             raise ValueError("expected frames of shape [N,3,%d,%d], got %s" %
                              (self.input_resolution, self.input_resolution, tuple(x.shape)))
@@ -222,25 +242,19 @@ class VisionTransformer(nn.Module):
                                      (l, (frame_offset + n) * seq, 3 * d, dev))
                 qkv[l] = buf.narrow(0, frame_offset * seq, n * seq)
         outs = {l: torch.empty((n, seq, d), dtype=torch.float32, device=dev) for l in range(self.layers)} if need_out else {}
+        plan = dict(n=n, dev=dev, x=x, qkv=qkv, outs=outs, run_layers=run_layers, qkv_only=1 if qkv_only else 0,
+                    packed=packed, dims=dims)
         if n == 0:
-            return qkv, outs
+            return plan
         ws_bytes = lib.dfd_encoder_workspace_bytes(ctypes.byref(dims), n)
-        ws = self._get_workspace(ws_bytes, dev)
+        plan["ws_bytes"], plan["ws"] = ws_bytes, self._get_workspace(ws_bytes, dev)
         qkv_arr = _native.ptr_array([qkv.get(l) for l in range(self.layers)])
         out_arr = _native.ptr_array([outs.get(l) for l in range(self.layers)]) if need_out else None
-        qkv_pp = ctypes.cast(qkv_arr, ctypes.POINTER(ctypes.c_void_p))
-        out_pp = ctypes.cast(out_arr, ctypes.POINTER(ctypes.c_void_p)) if need_out else None
-        with torch.cuda.device(dev):
-            if x.dtype == torch.uint8:
-                _native.check(lib.dfd_encoder_forward_u8(
-                    _native.ctx(dev), ctypes.byref(dims), _native.ptr(packed), _native.ptr(x),
-                    _native.mean_std_array(self.input_mean, self.input_std), n, run_layers, 1 if qkv_only else 0,
-                    qkv_pp, out_pp, _native.ptr(ws), ws_bytes, _native.stream_ptr(dev)))
-            else:
-                _native.check(lib.dfd_encoder_forward(
-                    _native.ctx(dev), ctypes.byref(dims), _native.ptr(packed), _native.ptr(x), n, run_layers,
-                    1 if qkv_only else 0, qkv_pp, out_pp, _native.ptr(ws), ws_bytes, _native.stream_ptr(dev)))
-        return qkv, outs
+        plan["keep_alive"] = (qkv_arr, out_arr)
+        plan["qkv_pp"] = ctypes.cast(qkv_arr, ctypes.POINTER(ctypes.c_void_p))
+        plan["out_pp"] = ctypes.cast(out_arr, ctypes.POINTER(ctypes.c_void_p)) if need_out else None
+        plan["mean_std"] = _native.mean_std_array(self.input_mean, self.input_std) if x.dtype == torch.uint8 else None
+        return plan
 
     def forward(self, x, with_out=False, with_q=False):
         n = x.shape[0]

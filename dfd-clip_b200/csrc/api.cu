@@ -106,6 +106,10 @@ int dfd_ctx_destroy(dfd_ctx* ctx) {
       cudaEventDestroy(s.start);
       cudaEventDestroy(s.stop);
     }
+    for (auto& e : ctx->tap_events) cudaEventDestroy(e);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    if (ctx->join_event) cudaEventDestroy(ctx->join_event);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   }
   delete ctx;
   return 0;

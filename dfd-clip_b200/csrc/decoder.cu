@@ -355,66 +355,84 @@ static DecWs carve_decoder_ws(void* base, int B, int T, int P, int D, int H, int
   return w;
 }
 
-int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
-                    const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
-                    float* video_feature, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  DFD_CHECK_ARG(D == 64 * H, "decoder_forward: width %d != 64 * heads %d", D, H);
-  DFD_CHECK_ARG(n_blocks > 0 && B >= 0 && T > 0 && P > 0, "decoder_forward: bad shape");
-  if (B == 0) return 0;  // empty batch: nothing to do (buffers of empty tensors are NULL)
-  DFD_CHECK_ARG(w && taps && mask && block_out && video_feature, "decoder_forward: null pointer");
-  DecWs ws = carve_decoder_ws(workspace, B, T, P, D, H, w->attn_mode);
-  if (!workspace || workspace_bytes < ws.total)
-    return fail(DFD_ERR_WORKSPACE, "decoder_forward: workspace %zu < %zu bytes", workspace_bytes, ws.total);
-  const int nthr = 256, nblk = (B * D + nthr - 1) / nthr;
 #define DFD_TIMED(tag, call)          \
   do {                                \
     ScopedTimer _t(ctx, tag, stream); \
     DFD_TRY(call);                    \
   } while (0)
 
+// The decoder as three steps, so that dfd_predict_forward can issue block i as soon as tapped layer i exists:
+// begin (query = ln_pre(class_embedding)), one call per block, end (ln_post).
+int DecoderRun::begin(cudaStream_t stream) {
+  DFD_CHECK_ARG(D == 64 * H, "decoder_forward: width %d != 64 * heads %d", D, H);
+  DFD_CHECK_ARG(n_blocks > 0 && B >= 0 && T > 0 && P > 0, "decoder_forward: bad shape");
+  if (B == 0) return 0;  // empty batch: nothing to do (buffers of empty tensors are NULL)
+  DFD_CHECK_ARG(w && taps && mask && block_out && video_feature, "decoder_forward: null pointer");
+  const DecWs ws = carve_decoder_ws(workspace, B, T, P, D, H, w->attn_mode);
+  if (!workspace || workspace_bytes < ws.total)
+    return fail(DFD_ERR_WORKSPACE, "decoder_forward: workspace %zu < %zu bytes", workspace_bytes, ws.total);
+  const int nthr = 256, nblk = (B * D + nthr - 1) / nthr;
   // x = ln_pre(class_embedding) repeated for every clip (models.py:336-337; dropout p = 0)
   DFD_TRY(layernorm(w->class_embedding, w->ln_pre_weight, w->ln_pre_bias, nullptr, 0, nullptr, ws.y, 1, D, stream));
   broadcast_rows_kernel<<<nblk, nthr, 0, stream>>>(ws.y, ws.x, B, D);
   DFD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
-  for (int i = 0; i < n_blocks; ++i) {
-    // x = x + out_proj(attn(in_proj(ln_1(x)), K_i, V_i, m))        (models.py:173-174, 136-146)
-    DFD_TIMED(DFD_TAG_DEC_OTHER,
-              layernorm(ws.x, w->ln_1_weight[i], w->ln_1_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.y, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, ws.qs, B,
-                                             2 * D, D, false, ws.lin, stream));
-    if (w->attn_mode) {
-      DFD_TIMED(DFD_TAG_DEC_ATTN,
-                decoder_attention_modes(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t,
-                                        taps->stride_p, w->positional_embedding, mask, B, T, P, H, w->attn_mode, ws.mix,
-                                        ws.part, dec_attn_modes_workspace_bytes(B, T, P, H), stream));
-    } else {
-      DFD_TIMED(DFD_TAG_DEC_ATTN,
-                decoder_attention(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
-                                  w->positional_embedding, mask, B, T, P, H, ws.mix, ws.part,
-                                  dec_attn_workspace_bytes(B, T, H), stream));
-    }
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.mix, w->out_proj_weight[i], w->out_proj_bias[i], ws.x, ws.x, B,
-                                             D, D, false, ws.lin, stream));
-    // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                     (models.py:175)
-    DFD_TIMED(DFD_TAG_DEC_OTHER,
-              layernorm(ws.x, w->ln_2_weight[i], w->ln_2_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
-    DFD_TIMED(DFD_TAG_DEC_LINEAR,
-              linear_f32(ctx, ws.y, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, ws.hid, B, 4 * D, D, true, ws.lin,
-                         stream));
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.hid, w->c_proj_weight[i], w->c_proj_bias[i], ws.x, ws.x, B, D,
-                                             4 * D, false, ws.lin, stream));
-    scatter_block_out_kernel<<<nblk, nthr, 0, stream>>>(ws.x, block_out, B, D, i, n_blocks);
-    DFD_CUDA_OK(cudaGetLastError());
-    if (w->augment_query && i + 1 < n_blocks) {  // models.py:265-267 (the recorded block output excludes it)
-      DFD_CHECK_ARG(w->augment_query[i] != nullptr, "decoder_forward: augment_query[%d] is NULL", i);
-      add_row_vector_kernel<<<nblk, nthr, 0, stream>>>(ws.x, w->augment_query[i], B, D);
-      DFD_CUDA_OK(cudaGetLastError());
-    }
+int DecoderRun::block(int i, cudaStream_t stream) {
+  if (B == 0) return 0;
+  const DecWs ws = carve_decoder_ws(workspace, B, T, P, D, H, w->attn_mode);
+  const int nthr = 256, nblk = (B * D + nthr - 1) / nthr;
+  // x = x + out_proj(attn(in_proj(ln_1(x)), K_i, V_i, m))        (models.py:173-174, 136-146)
+  DFD_TIMED(DFD_TAG_DEC_OTHER,
+            layernorm(ws.x, w->ln_1_weight[i], w->ln_1_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
+  DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.y, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, ws.qs, B,
+                                           2 * D, D, false, ws.lin, stream));
+  if (w->attn_mode) {
+    DFD_TIMED(DFD_TAG_DEC_ATTN,
+              decoder_attention_modes(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t,
+                                      taps->stride_p, w->positional_embedding, mask, B, T, P, H, w->attn_mode, ws.mix,
+                                      ws.part, dec_attn_modes_workspace_bytes(B, T, P, H), stream));
+  } else {
+    DFD_TIMED(DFD_TAG_DEC_ATTN,
+              decoder_attention(ctx, ws.qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
+                                w->positional_embedding, mask, B, T, P, H, ws.mix, ws.part,
+                                dec_attn_workspace_bytes(B, T, H), stream));
   }
+  DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.mix, w->out_proj_weight[i], w->out_proj_bias[i], ws.x, ws.x, B, D,
+                                           D, false, ws.lin, stream));
+  // x = x + c_proj(quickgelu(c_fc(ln_2(x))))                     (models.py:175)
+  DFD_TIMED(DFD_TAG_DEC_OTHER,
+            layernorm(ws.x, w->ln_2_weight[i], w->ln_2_bias[i], nullptr, 0, nullptr, ws.y, B, D, stream));
+  DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.y, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, ws.hid, B, 4 * D, D,
+                                           true, ws.lin, stream));
+  DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, ws.hid, w->c_proj_weight[i], w->c_proj_bias[i], ws.x, ws.x, B, D,
+                                           4 * D, false, ws.lin, stream));
+  scatter_block_out_kernel<<<nblk, nthr, 0, stream>>>(ws.x, block_out, B, D, i, n_blocks);
+  DFD_CUDA_OK(cudaGetLastError());
+  if (w->augment_query && i + 1 < n_blocks) {  // models.py:265-267 (the recorded block output excludes it)
+    DFD_CHECK_ARG(w->augment_query[i] != nullptr, "decoder_forward: augment_query[%d] is NULL", i);
+    add_row_vector_kernel<<<nblk, nthr, 0, stream>>>(ws.x, w->augment_query[i], B, D);
+    DFD_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int DecoderRun::end(cudaStream_t stream) {
+  if (B == 0) return 0;
+  const DecWs ws = carve_decoder_ws(workspace, B, T, P, D, H, w->attn_mode);
   // video_feature = ln_post(x_last)                                  (models.py:340-343)
   DFD_TRY(layernorm(ws.x, w->ln_post_weight, w->ln_post_bias, nullptr, 0, nullptr, video_feature, B, D, stream));
   return 0;
+}
+
+int decoder_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
+                    const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
+                    float* video_feature, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DecoderRun run{ctx, D, H, n_blocks, w, taps, mask, B, T, P, block_out, video_feature, workspace, workspace_bytes};
+  DFD_TRY(run.begin(stream));
+  for (int i = 0; i < n_blocks; ++i) DFD_TRY(run.block(i, stream));
+  return run.end(stream);
 }
 
 }  // namespace dfd

@@ -13,6 +13,8 @@
 #include "host_common.h"
 #include <stdlib.h>
 
+#include <functional>
+
 namespace dfd {
 
 int gemm_bf16(const dfd_ctx* ctx, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
@@ -194,7 +196,10 @@ int encoder_pack_weights(const dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd
 
 int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
                     const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
-                    float* const* x_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                    float* const* x_out, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                    const std::function<int(int)>& after_qkv = {}) {
+  // after_qkv(layer): called right after the launch of that layer's K/V (QKV) projection, i.e. as soon as everything a
+  // tap of the layer consists of has been enqueued (dfd_predict_forward issues the decoder block of that tap from it)
   VitShape s;
   DFD_TRY(vit_shape(dims, &s));
   DFD_CHECK_ARG(n_frames >= 0, "encoder_forward: negative frame count");
@@ -259,11 +264,13 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
                 gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_in + static_cast<size_t>(D) * D * 2, D, f32p(lb + pl.bf_in) + D,
                              static_cast<uint8_t*>(qkv) + static_cast<size_t>(D) * 2, 3 * D, M, 2 * D, D,
                              DFD_EPI_STORE_BF16_LNFOLD, &fold_in, stream));
+      if (after_qkv) DFD_TRY(after_qkv(l));
       break;
     }
     fold_in.colsum = f32p(lb + pl.c_in);
     DFD_TIMED(DFD_TAG_GEMM_QKV, gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_in, D, f32p(lb + pl.bf_in), qkv, 3 * D, M,
                                              3 * D, D, DFD_EPI_STORE_BF16_LNFOLD, &fold_in, stream));
+    if (after_qkv) DFD_TRY(after_qkv(l));
     DFD_TIMED(DFD_TAG_MHA, mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
     DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16_ln(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
                                              DFD_EPI_RESID_LN_F32, &resid, stream));
@@ -289,10 +296,12 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
                 gemm_bf16(ctx, u, D, pk + lb + pl.w_in + static_cast<size_t>(D) * D * 2, D, f32p(lb + pl.b_in) + D,
                           static_cast<uint8_t*>(qkv) + static_cast<size_t>(D) * 2, 3 * D, M, 2 * D, D,
                           DFD_EPI_STORE_BF16, stream));
+      if (after_qkv) DFD_TRY(after_qkv(l));
       break;
     }
     DFD_TIMED(DFD_TAG_GEMM_QKV, gemm_bf16(ctx, u, D, pk + lb + pl.w_in, D, f32p(lb + pl.b_in), qkv, 3 * D, M, 3 * D, D,
                                           DFD_EPI_STORE_BF16, stream));
+    if (after_qkv) DFD_TRY(after_qkv(l));
     DFD_TIMED(DFD_TAG_MHA, mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
     // x = x + out_proj(mix)
     DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
@@ -310,9 +319,95 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
   return 0;
 }
 
+// Side stream and events of the overlapped predict (created once per context).
+static int ensure_side_stream(const dfd_ctx* ctx, int n_events) {
+  if (!ctx->side_stream) {
+    int lo = 0, hi = 0;
+    DFD_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
+    DFD_CUDA_OK(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+    DFD_CUDA_OK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    DFD_CUDA_OK(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
+  }
+  while (static_cast<int>(ctx->tap_events.size()) < n_events) {
+    cudaEvent_t e;
+    DFD_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->tap_events.push_back(e);
+  }
+  return 0;
+}
+
+// Detector.predict (src/models.py:498-566) as ONE call: the encoder on `stream`, and decoder block i on the
+// context's side stream as soon as the K/V projection of its tapped layer has been enqueued, so that the one-token
+// decoder (launch- and HBM-bound) runs beside the tensor-bound encoder layers that follow the tap. Fork/join with
+// events, so the call is CUDA-graph capturable and `stream` ends up ordered after the whole decoder.
+int predict_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
+                    const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                    void* enc_workspace, size_t enc_workspace_bytes, DecoderRun run, const int* tap_layers,
+                    int overlap, cudaStream_t stream) {
+  DFD_CHECK_ARG(tap_layers != nullptr && run.n_blocks > 0, "predict_forward: tap_layers is NULL or no decoder blocks");
+  for (int i = 0; i < run.n_blocks; ++i)
+    DFD_CHECK_ARG(tap_layers[i] >= 0 && tap_layers[i] < num_run_layers,
+                  "predict_forward: tap %d is layer %d but only layers [0, %d) run", i, tap_layers[i], num_run_layers);
+  if (n_frames == 0 || run.B == 0) return 0;
+  // per-kernel timing wants every kernel alone on the device: no overlap while it is on
+  if (!overlap || ctx->timing) {
+    DFD_TRY(encoder_forward(ctx, dims, packed, frames, mean_std, n_frames, num_run_layers, last_qkv_only, qkv_out,
+                            nullptr, enc_workspace, enc_workspace_bytes, stream));
+    DFD_TRY(run.begin(stream));
+    for (int i = 0; i < run.n_blocks; ++i) DFD_TRY(run.block(i, stream));
+    return run.end(stream);
+  }
+  DFD_TRY(ensure_side_stream(ctx, run.n_blocks));
+  cudaStream_t side = ctx->side_stream;
+  DFD_CUDA_OK(cudaEventRecord(ctx->fork_event, stream));
+  DFD_CUDA_OK(cudaStreamWaitEvent(side, ctx->fork_event, 0));
+  int rc = run.begin(side);
+  int next = 0;  // blocks are sequential (block i consumes block i-1's query): issue them in order, each once its
+                 // layer (and every earlier block's layer) has been projected
+  if (rc == 0)
+    rc = encoder_forward(ctx, dims, packed, frames, mean_std, n_frames, num_run_layers, last_qkv_only, qkv_out, nullptr,
+                         enc_workspace, enc_workspace_bytes, stream, [&](int layer) -> int {
+                           while (next < run.n_blocks && tap_layers[next] <= layer) {
+                             DFD_CUDA_OK(cudaEventRecord(ctx->tap_events[next], stream));
+                             DFD_CUDA_OK(cudaStreamWaitEvent(side, ctx->tap_events[next], 0));
+                             DFD_TRY(run.block(next, side));
+                             ++next;
+                           }
+                           return 0;
+                         });
+  if (rc == 0 && next != run.n_blocks)
+    rc = fail(DFD_ERR_INVALID, "predict_forward: %d of %d decoder blocks issued", next, run.n_blocks);
+  if (rc == 0) rc = run.end(side);
+  // always join: a failed call must not leave the side stream forked (a graph capture would be invalidated)
+  cudaError_t e1 = cudaEventRecord(ctx->join_event, side);
+  cudaError_t e2 = cudaStreamWaitEvent(stream, ctx->join_event, 0);
+  if (rc != 0) return rc;
+  DFD_CUDA_OK(e1);
+  DFD_CUDA_OK(e2);
+  return 0;
+}
+
 }  // namespace dfd
 
 extern "C" {
+
+int dfd_predict_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
+                        int frames_are_u8, const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only,
+                        void* const* qkv_out, void* enc_workspace, size_t enc_workspace_bytes, int D, int H,
+                        int n_blocks, const dfd_decoder_weights* w, const dfd_kv_taps* taps, const int* tap_layers,
+                        const uint8_t* mask, int B, int T, int P, float* block_out, float* video_feature,
+                        void* dec_workspace, size_t dec_workspace_bytes, int overlap, void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_predict_forward: ctx is NULL");
+  if (frames_are_u8 && !mean_std) return dfd::fail(DFD_ERR_INVALID, "dfd_predict_forward: mean_std is NULL");
+  if (static_cast<int64_t>(B) * T != n_frames)
+    return dfd::fail(DFD_ERR_INVALID, "dfd_predict_forward: %d clips x %d frames != %d frames", B, T, n_frames);
+  dfd::DecoderRun run{ctx, D, H, n_blocks, w, taps, mask, B, T, P, block_out, video_feature, dec_workspace,
+                      dec_workspace_bytes};
+  return dfd::predict_forward(ctx, dims, packed, frames, frames_are_u8 ? mean_std : nullptr, n_frames, num_run_layers,
+                              last_qkv_only, qkv_out, enc_workspace, enc_workspace_bytes, run, tap_layers, overlap,
+                              static_cast<cudaStream_t>(stream));
+}
 
 size_t dfd_encoder_packed_bytes(const dfd_vit_dims* dims) {
   dfd::VitShape s;

@@ -44,9 +44,32 @@ struct dfd_ctx {
   mutable bool timing = false;
   mutable std::vector<dfd_timing_slot> slots;
   mutable size_t slots_used = 0;
+  // dfd_predict_forward: the decoder blocks run on this stream beside the encoder layers that follow their tap
+  // (created on first use; high priority so that the small decoder kernels are placed as soon as SMs free up)
+  mutable cudaStream_t side_stream = nullptr;
+  mutable cudaEvent_t fork_event = nullptr, join_event = nullptr;
+  mutable std::vector<cudaEvent_t> tap_events;
 };
 
 namespace dfd {
+
+// One decoder pass split into steps (decoder.cu); dfd_decoder_forward runs them back to back on one stream,
+// dfd_predict_forward issues block i on the context's side stream as soon as the encoder has produced tap i.
+struct DecoderRun {
+  const dfd_ctx* ctx;
+  int D, H, n_blocks;
+  const dfd_decoder_weights* w;
+  const dfd_kv_taps* taps;
+  const uint8_t* mask;
+  int B, T, P;
+  float* block_out;
+  float* video_feature;
+  void* workspace;
+  size_t workspace_bytes;
+  int begin(cudaStream_t stream);
+  int block(int i, cudaStream_t stream);
+  int end(cudaStream_t stream);
+};
 
 // Thread-local last-error string (dfd_last_error). Returns `code` so callers can `return fail(...)`.
 int fail(int code, const char* fmt, ...);

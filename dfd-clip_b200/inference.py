@@ -109,6 +109,112 @@ class HostClipPipeline:
         return out_host
 
 
+class HostClipStream:
+    """Batch-after-batch scoring of host-resident clips, pipelined ACROSS batches (the reference's caller loop,
+    inference.py:107-156, issues a blocking ``.to(device)``, a full ``predict`` and a blocking ``.to("cpu")`` per
+    chunk). Three streams work on up to three batches at once:
+
+    * copy stream:    H2D of batch k+1 (one whole-batch copy into the free one of two device input buffers),
+    * main stream:    encoder of batch k (one full-size pass: no chunking, the GEMMs keep their full M),
+    * decoder stream: decoder + logit normalisation of batch k-1 and the D2H copy of its logits
+      (``overlap_decoder``; the decoder is one query token per clip, launch/HBM-bound, and reads its own of two sets
+      of tap buffers, so it can run beside the next batch's tensor-bound encoder).
+
+    ``run`` is a generator: it yields one host tensor of task-0 logits per input batch, in order, one batch behind the
+    batch being issued. Results are bit-identical to ``Detector.predict`` on the same clips (same kernels, same
+    launch shapes)."""
+
+    def __init__(self, detector, overlap_decoder=True):
+        self.det = detector
+        self.dev = next(detector.decoder.parameters()).device
+        if self.dev.type != "cuda":
+            raise RuntimeError("HostClipStream needs the detector on a CUDA device")
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.dec_stream = torch.cuda.Stream(self.dev, priority=-1) if overlap_decoder else None
+        self._x = [None, None]     # device input buffers (fp32 or uint8)
+        self._m = [None, None]     # device masks
+        self._taps = [None, None]  # per-slot tap buffers {layer: bf16 [rows, 3D]}
+        self._out = [None, None]   # pinned host logits
+
+    def _slot_buffers(self, slot, x_host, m_host):
+        n, t = x_host.shape[:2]
+        # The copy stream is the first writer of the input buffers, so they come from ITS allocator pool: a block
+        # handed out on the main stream may still be written by main-stream kernels that were launched (and whose
+        # tensors were freed) earlier, which the copy stream does not wait for.
+        with torch.cuda.stream(self.copy_stream):
+            xb = self._x[slot]
+            if xb is None or xb.dtype != x_host.dtype or xb.shape[1:] != x_host.shape[1:] or xb.shape[0] < n:
+                self._x[slot] = None
+                xb = self._x[slot] = torch.empty(tuple(x_host.shape), dtype=x_host.dtype, device=self.dev)
+            mb = self._m[slot]
+            if mb is None or mb.shape[1:] != m_host.shape[1:] or mb.shape[0] < n or mb.dtype != m_host.dtype:
+                mb = self._m[slot] = torch.empty(tuple(m_host.shape), dtype=m_host.dtype, device=self.dev)
+        enc = self.det.encoder
+        rows, cols = n * t * enc.tokens_per_frame, 3 * enc.width
+        tap_slot = slot if self.dec_stream is not None else 0  # one stream -> the decoder is done before the next encoder
+        taps = self._taps[tap_slot]
+        if taps is None or next(iter(taps.values())).shape[0] < rows:
+            self._taps[tap_slot] = None
+            taps = self._taps[tap_slot] = {l: torch.empty((rows, cols), dtype=torch.bfloat16, device=self.dev)
+                                           for l in self.det.layer_indices}
+        ob = self._out[slot]
+        out_dim = self.det.out_dim[0]
+        if ob is None or ob.shape[0] < n:
+            ob = self._out[slot] = torch.empty((n, out_dim), dtype=torch.float32).pin_memory()
+        return xb, mb, taps, ob
+
+    def _issue(self, slot, x_host, m_host):
+        """Enqueue copy, encoder and decoder of one batch; returns (event after the D2H copy, pinned logits view)."""
+        n, t = x_host.shape[:2]
+        det, main = self.det, torch.cuda.current_stream(self.dev)
+        xb, mb, taps, ob = self._slot_buffers(slot, x_host, m_host)
+        copied, done = torch.cuda.Event(), torch.cuda.Event()
+        # the slot's buffers are free: the batch that used them (two back) was synchronised before this call
+        with torch.cuda.stream(self.copy_stream):
+            xb[:n].copy_(x_host, non_blocking=True)
+            mb[:n].copy_(m_host, non_blocking=True)
+            copied.record(self.copy_stream)
+        main.wait_event(copied)
+        det.encoder.encode(xb[:n].flatten(0, 1), keep_layers=det.layer_indices, qkv_into=taps)
+        tail = main
+        if self.dec_stream is not None:
+            encoded = torch.cuda.Event()
+            encoded.record(main)
+            self.dec_stream.wait_event(encoded)
+            tail = self.dec_stream
+        with torch.cuda.stream(tail), torch.no_grad():
+            logits, _ = det.predict_from_taps(taps, mb[:n], n, t)
+            ob[:n].copy_(logits[0], non_blocking=True)
+            done.record(tail)
+        return done, ob[:n]
+
+    def run(self, batches):
+        """``batches``: iterable of ``(x_host, m_host)`` (x fp32 normalised or uint8 ``[B,T,3,R,R]``, m bool ``[B,T]``,
+        pinned for real overlap). Yields fp32 ``[B, out_dim]`` host tensors (task 0), one per batch, in order."""
+        pending = None
+        out_dim = self.det.out_dim[0]
+        for k, (x_host, m_host) in enumerate(batches):
+            if x_host.shape[0] == 0:
+                cur = (None, torch.empty((0, out_dim), dtype=torch.float32))
+            else:
+                cur = self._issue(k % 2, x_host, m_host)
+            if pending is not None:
+                if pending[0] is not None:
+                    pending[0].synchronize()
+                yield pending[1].clone()
+            pending = cur
+        if pending is not None:
+            if pending[0] is not None:
+                pending[0].synchronize()
+            yield pending[1].clone()
+
+
+def predict_stream(detector, batches, overlap_decoder=True):
+    """Generator over ``HostClipStream.run``: host batches in, host logits out, H2D / encoder / decoder+D2H of
+    consecutive batches overlapped."""
+    yield from HostClipStream(detector, overlap_decoder=overlap_decoder).run(batches)
+
+
 _PIPELINES = {}
 
 
@@ -144,11 +250,49 @@ def video_mean_probs(clip_logits, clip_counts):
     return sums / counts.clamp_min(1).unsqueeze(1).to(probs.dtype)
 
 
+def pack_clip_batches(videos, masks, batch_clips=64, pin=None):
+    """Generator: the clips of ``videos`` (host tensors ``[n_i, T, 3, R, R]``, any mix of lengths, zero allowed) packed
+    in order into batches of ``batch_clips`` clips, video boundaries ignored. Each batch is a view of one of TWO rotating
+    staging buffers (pinned when CUDA is available, so the H2D copy of ``HostClipStream`` is asynchronous) — a consumer
+    may hold a batch only until it asks for the batch after the next one, which is exactly what ``HostClipStream.run``
+    does (batch k-2 has been synchronised before batch k is requested). Nothing is concatenated or pinned up front:
+    host memory beyond the caller's videos is two batches."""
+    step = max(1, int(batch_clips))
+    first = next((v for v in videos if v.shape[0] > 0), None)
+    if first is None:
+        return
+    if pin is None:
+        pin = torch.cuda.is_available()
+    m_first = next(m for v, m in zip(videos, masks) if v.shape[0] > 0)
+    stage_x = [torch.empty((step,) + tuple(first.shape[1:]), dtype=first.dtype, pin_memory=pin) for _ in range(2)]
+    stage_m = [torch.empty((step,) + tuple(m_first.shape[1:]), dtype=m_first.dtype, pin_memory=pin) for _ in range(2)]
+    slot, fill = 0, 0
+    for v, m in zip(videos, masks):
+        if v.shape[1:] != first.shape[1:] or v.dtype != first.dtype:
+            raise ValueError("all videos must share one clip shape and dtype: %s %s vs %s %s" %
+                             (tuple(v.shape[1:]), v.dtype, tuple(first.shape[1:]), first.dtype))
+        if m.shape[0] != v.shape[0]:
+            raise ValueError("mask rows %d != clips %d" % (m.shape[0], v.shape[0]))
+        a, n = 0, int(v.shape[0])
+        while a < n:
+            take = min(step - fill, n - a)
+            stage_x[slot][fill:fill + take].copy_(v[a:a + take])
+            stage_m[slot][fill:fill + take].copy_(m[a:a + take])
+            fill += take
+            a += take
+            if fill == step:
+                yield stage_x[slot], stage_m[slot]
+                slot, fill = 1 - slot, 0
+    if fill:
+        yield stage_x[slot][:fill], stage_m[slot][:fill]
+
+
 def score_videos_batched(detector, videos, masks, batch_clips=64, group=None):
     """The same result as ``score_videos`` for host-resident videos, computed the way the hardware likes it: the
     clips of ALL of this rank's videos are packed into batches of ``batch_clips`` (video boundaries do not matter:
-    clips are independent) and pushed through ``HostClipPipeline`` (H2D double-buffered under the encoder, decoder once
-    per batch, one D2H of the logits); the per-video mean of clip probabilities is a segment mean at the end and ONE
+    clips are independent) by ``pack_clip_batches`` (two rotating pinned staging buffers) and pushed through
+    ``HostClipStream`` (packing + H2D of the next batch, encoder of this one and decoder + D2H of the previous one in
+    flight together); the per-video mean of clip probabilities is a segment mean at the end and ONE
     all_gather assembles the ranks' scores. The reference scores one video at a time in chunks of 16 clips with a
     blocking copy in each direction per chunk (inference.py:107-156).
 
@@ -165,13 +309,9 @@ def score_videos_batched(detector, videos, masks, batch_clips=64, group=None):
     out_dim = detector.out_dim[0]
     result = torch.full((len(videos), out_dim), float("nan"), device=dev)
     if mine:
-        x_host = torch.cat([videos[i] for i in mine])
-        m_host = torch.cat([masks[i] for i in mine])
-        if not x_host.is_pinned():
-            x_host, m_host = x_host.pin_memory(), m_host.pin_memory()
-        pipe = HostClipPipeline(detector)
-        pipe.MAX_BATCH = int(batch_clips)
-        logits = pipe(x_host, m_host).to(dev)
+        pipe = HostClipStream(detector)
+        batches = pack_clip_batches([videos[i] for i in mine], [masks[i] for i in mine], batch_clips)
+        logits = torch.cat(list(pipe.run(batches))).to(dev)
         rows = video_mean_probs(logits, [counts[i] for i in mine])
     else:
         rows = torch.empty((0, out_dim), device=dev)

@@ -11,6 +11,7 @@ which the reference itself cannot execute) raises ``NotImplementedError`` instea
 CPU / PyTorch fallback for the encoder, the adapter's inference path or the decoder attention.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -292,6 +293,19 @@ class Decoder(nn.Module):
     def run(self, kvs, m, logit_scale=0.0):
         """``forward`` with the logit normalisation of ``Detector.predict`` (:551-553) fused into the projection
         kernel when ``logit_scale`` > 0."""
+        plan = self._run_plan(kvs, m)
+        lib, dev = _native.load_library(), plan["dev"]
+        with torch.cuda.device(dev):
+            _native.check(lib.dfd_decoder_forward(
+                _native.ctx(dev), self.width, self.heads, plan["nb"], ctypes.byref(plan["w"]),
+                ctypes.byref(plan["taps"]), _native.ptr(plan["mask"]), plan["b"], plan["t"], plan["p"],
+                _native.ptr(plan["block_out"]), _native.ptr(plan["video_feature"]), _native.ptr(plan["ws"]),
+                plan["ws_bytes"], _native.stream_ptr(dev)))
+        return self._finish(plan, logit_scale)
+
+    def _run_plan(self, kvs, m):
+        """Argument checking, output / workspace buffers and pointer structs of one decoder pass (everything ``run``
+        does short of the launch; ``Detector.predict`` hands the same plan to ``dfd_predict_forward``)."""
         if len(kvs) != len(self.transformer.resblocks):
             raise ValueError("expected %d tapped layers, got %d" % (len(self.transformer.resblocks), len(kvs)))
         k0 = kvs[0]["k"]
@@ -306,6 +320,7 @@ class Decoder(nn.Module):
             raise _native.NativeError("dfdclip_b200 decoder needs CUDA tensors (no CPU fallback)")
         strides = None
         ks, vs, keep = [], [], []
+        copied = False
         for kv in kvs:
             pair = []
             for name in ("k", "v"):
@@ -315,6 +330,7 @@ class Decoder(nn.Module):
                       and (strides is None or ten.stride()[:3] == strides))
                 if not ok:
                     ten = ten.to(torch.bfloat16).contiguous()
+                    copied = True
                     if strides is not None and ten.stride()[:3] != strides:
                         raise ValueError("all tapped K/V tensors must share one layout")
                 if strides is None:
@@ -337,11 +353,15 @@ class Decoder(nn.Module):
         ws_bytes = lib.dfd_decoder_workspace_bytes(b, t, p, d, nb, self.attn_mode)
         if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
             self._workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        return dict(dev=dev, b=b, t=t, p=p, nb=nb, w=w, taps=taps, mask=mask, block_out=block_out,
+                    video_feature=video_feature, ws=self._workspace, ws_bytes=ws_bytes, copied=copied,
+                    keep_alive=(keep, karr, varr))
+
+    def _finish(self, plan, logit_scale):
+        """Task projections (+ ln_post over every block for op_mode.global_prediction) after the decoder pass."""
+        dev, b, nb, d = plan["dev"], plan["b"], plan["nb"], self.width
+        block_out, video_feature = plan["block_out"], plan["video_feature"]
         with torch.cuda.device(dev):
-            _native.check(lib.dfd_decoder_forward(
-                _native.ctx(dev), d, self.heads, nb, ctypes.byref(w), ctypes.byref(taps), _native.ptr(mask), b, t, p,
-                _native.ptr(block_out), _native.ptr(video_feature), _native.ptr(self._workspace), ws_bytes,
-                _native.stream_ptr(dev)))
             if self.global_prediction:
                 # ln_post over every block output, then sum_j c_j (f_j @ P_j) = [f_0 | f_1 | ...] @ vstack(c_j P_j)
                 video_feature = _native.layernorm(block_out.view(b * nb, d), self.ln_post.weight.detach(),
@@ -624,10 +644,45 @@ class Detector(nn.Module):
         if with_adapt_features and self.adapter is None:
             raise Exception("cannot return adaptive features without an adapter")
         b, t = x.shape[:2]
+        if self._single_call_ok(train) and b > 0:
+            return self._predict_single_call(x, m, with_video_features)
         with torch.no_grad():
             qkv, _ = self.encoder.encode(x.flatten(0, 1), keep_layers=self.layer_indices)
         return self.predict_from_taps(qkv, m, b, t, with_video_features=with_video_features,
                                       with_adapt_features=with_adapt_features, train=train)
+
+    def _single_call_ok(self, train):
+        """Inference without an adapter goes through ``dfd_predict_forward`` (encoder and decoder in one native call,
+        decoder blocks overlapped with the encoder layers after their tap); everything that needs autograd, the adapter
+        between taps and decoder, or a patch gather keeps the two-call path. ``DFD_OVERLAP=0`` switches it off."""
+        if self.adapter is not None or os.environ.get("DFD_OVERLAP", "1") == "0":
+            return False
+        if train and "patch_mask" in self.train_mode:
+            return False
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()):
+            return False
+        return not (self.decoder.training and self.decoder.dropout > 0)
+
+    def _predict_single_call(self, x, m, with_video_features=False):
+        b, t = x.shape[:2]
+        enc, dec = self.encoder, self.decoder
+        with torch.no_grad():
+            ep = enc._encode_plan(x.flatten(0, 1), keep_layers=self.layer_indices)
+            dp = dec._run_plan(self.taps_from_qkv(ep["qkv"], b, t), m)
+            if dp["copied"]:  # cannot happen for views of the packed buffers; the decoder would read stale copies
+                raise _native.NativeError("single-call predict needs the decoder to read the taps in place")
+            lib, dev = _native.load_library(), ep["dev"]
+            tap_layers = (ctypes.c_int * len(self.layer_indices))(*self.layer_indices)
+            with torch.cuda.device(dev):
+                _native.check(lib.dfd_predict_forward(
+                    _native.ctx(dev), ctypes.byref(ep["dims"]), _native.ptr(ep["packed"]), _native.ptr(ep["x"]),
+                    1 if ep["x"].dtype == torch.uint8 else 0, ep["mean_std"], ep["n"], ep["run_layers"], ep["qkv_only"],
+                    ep["qkv_pp"], _native.ptr(ep["ws"]), ep["ws_bytes"], dec.width, dec.heads, dp["nb"],
+                    ctypes.byref(dp["w"]), ctypes.byref(dp["taps"]), tap_layers, _native.ptr(dp["mask"]), dp["b"],
+                    dp["t"], dp["p"], _native.ptr(dp["block_out"]), _native.ptr(dp["video_feature"]),
+                    _native.ptr(dp["ws"]), dp["ws_bytes"], 1, _native.stream_ptr(dev)))
+            task_logits, video_features = dec._finish(dp, 5.0)
+        return task_logits, ({"video": video_features} if with_video_features else {})
 
     def taps_from_qkv(self, qkv, b, t):
         """Views of the packed per-layer QKV buffers as the decoder's ``[{k, v: [B,T,P,H,64]}]`` list: CLS token

@@ -226,6 +226,21 @@ int dfd_decoder_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_deco
                         const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
                         float* video_feature, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Detector.predict (src/models.py:498-566: encoder, taps, decoder) as ONE call = dfd_encoder_forward[_u8] +
+ * dfd_decoder_forward with the same arguments, except that with overlap != 0 decoder block i is launched on a stream
+ * owned by the context as soon as the K/V projection of encoder layer tap_layers[i] has been enqueued, so the
+ * one-token decoder (launch/HBM-bound) runs beside the tensor-bound encoder layers that follow its tap. `stream` is
+ * joined with that stream before the call returns (event fork/join: CUDA-graph capturable); results are bit-identical
+ * to the two separate calls. frames: fp32 [n_frames,3,R,R], or uint8 with frames_are_u8 != 0 (then mean_std as in
+ * dfd_encoder_forward_u8). tap_layers: HOST array [n_blocks], taps->k[i] / v[i] must point into qkv_out[tap_layers[i]].
+ * n_frames must equal B*T. While per-kernel timing is enabled (dfd_timing_enable) the call runs without overlap. */
+int dfd_predict_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
+                        int frames_are_u8, const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only,
+                        void* const* qkv_out, void* enc_workspace, size_t enc_workspace_bytes, int D, int H,
+                        int n_blocks, const dfd_decoder_weights* w, const dfd_kv_taps* taps, const int* tap_layers,
+                        const uint8_t* mask, int B, int T, int P, float* block_out, float* video_feature,
+                        void* dec_workspace, size_t dec_workspace_bytes, int overlap, void* stream);
+
 /* logits[b,:] = scale * l / (||l||_2 + 1e-10), l = feature[b,:] @ proj[D,O] (models.py:359, 551-553).
  * scale <= 0 skips the normalisation. */
 int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, int B, int D, int O, float scale,

@@ -268,3 +268,32 @@ def test_chunk_schedule_covers_batch():
     assert chunk_schedule(0) == []
     for n in range(0, 150, 7):
         assert sum(chunk_schedule(n)) == n and all(c > 0 for c in chunk_schedule(n))
+
+
+def test_pack_clip_batches_packs_in_order_across_video_boundaries():
+    """The host-side packer of the video-level driver: clips of videos of unequal length (empty ones included) come
+    out in order in batches of `batch_clips`, each batch a view of one of two rotating staging buffers that stays
+    intact until the batch after the next one is requested (the contract HostClipStream relies on)."""
+    from dfdclip_b200.inference import pack_clip_batches
+    g = torch.Generator().manual_seed(0)
+    counts = [5, 0, 1, 9, 2, 0, 7]
+    videos = [torch.randint(0, 256, (n, 2, 3, 4, 4), generator=g, dtype=torch.uint8) for n in counts]
+    masks = [torch.rand((n, 2), generator=g) > 0.3 for n in counts]
+    all_x, all_m = torch.cat(videos), torch.cat(masks)
+    for step in (1, 4, 7, 24, 100):
+        seen_x, seen_m, prev = [], [], None
+        for xb, mb in pack_clip_batches(videos, masks, step, pin=False):
+            assert 0 < xb.shape[0] <= step and xb.shape[0] == mb.shape[0]
+            if prev is not None:  # the previous batch is still intact while this one exists
+                assert torch.equal(prev[0], prev[1])
+                seen_x.append(prev[1])
+            prev = (xb, xb.clone())
+            seen_m.append(mb.clone())
+        seen_x.append(prev[1])
+        assert torch.equal(torch.cat(seen_x), all_x)
+        assert torch.equal(torch.cat(seen_m), all_m)
+        sizes = [t.shape[0] for t in seen_x]
+        assert all(s == step for s in sizes[:-1]) and sum(sizes) == sum(counts)
+    assert list(pack_clip_batches([videos[1]], [masks[1]], 4, pin=False)) == []
+    with pytest.raises(ValueError):
+        list(pack_clip_batches([videos[0], videos[0].float()], [masks[0], masks[0]], 4, pin=False))

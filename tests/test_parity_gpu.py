@@ -191,6 +191,71 @@ def test_predict_from_host_matches_predict(cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("u8", [False, True])
+def test_predict_stream_matches_predict(cuda_device, overlap, u8):
+    """The cross-batch pipeline (copy stream / encoder / decoder stream, two slots) yields, batch by batch and in
+    order, logits bit-identical to predict() on the same clips: ragged batch sizes (buffers shrink and grow), an empty
+    batch in the middle, more batches than slots, fp32 and raw uint8 clips."""
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.inference import HostClipStream
+    arch, frames = "small-512x6", 3
+    det, _ = build_detector(arch, frames, [0, 2, 4], cuda_device)
+    res = synthetic.vit_dims(arch)["image_size"]
+    sizes = [5, 2, 0, 7, 7, 1, 6]
+    batches = []
+    for i, n in enumerate(sizes):
+        x, m = synthetic.make_clips(max(n, 1), frames, res, seed=40 + i)
+        if u8:
+            x = torch.randint(0, 256, tuple(x.shape), generator=torch.Generator().manual_seed(90 + i), dtype=torch.uint8)
+        batches.append((x[:n].pin_memory(), m[:n].pin_memory()))
+    want = []
+    for x, m in batches:
+        if x.shape[0] == 0:
+            want.append(torch.empty((0, 2)))
+        else:
+            want.append(det.predict(x.to(cuda_device), m.to(cuda_device))[0][0].cpu())
+    pipe = HostClipStream(det, overlap_decoder=overlap)
+    for _ in range(2):  # second pass reuses the slot buffers
+        got = list(pipe.run(iter(batches)))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and torch.equal(g, w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("taps", [[0, 2, 4], [3, 4, 5], [4, 0, 2], [1, 1, 5]])
+def test_single_call_predict_is_bit_identical_to_the_two_call_path(cuda_device, monkeypatch, taps):
+    """dfd_predict_forward (decoder blocks on the context's side stream, each released by an event behind its tap's
+    K/V projection) against dfd_encoder_forward followed by dfd_decoder_forward on one stream: same kernels, same
+    arguments, so logits and video features must be bit-identical — also for taps that are not ascending or repeat a
+    layer, for uint8 frames, for masked frames, and when called again and again without a host sync in between."""
+    from dfdclip_b200 import synthetic
+    arch, frames, clips = "small-512x6", 3, 9
+    det, _ = build_detector(arch, frames, taps, cuda_device, decode_indices=taps)
+    res = synthetic.vit_dims(arch)["image_size"]
+    x, m = synthetic.make_clips(clips, frames, res, seed=5)
+    x8 = torch.randint(0, 256, tuple(x.shape), generator=torch.Generator().manual_seed(6), dtype=torch.uint8)
+    assert not m.all()
+    for inp in (x.to(cuda_device), x8.to(cuda_device)):
+        md = m.to(cuda_device)
+        with torch.no_grad():
+            monkeypatch.setenv("DFD_OVERLAP", "0")
+            assert not det._single_call_ok(False)
+            ref_logits, ref_feats = det.predict(inp, md, with_video_features=True)
+            monkeypatch.setenv("DFD_OVERLAP", "1")
+            assert det._single_call_ok(False)
+            runs = [det.predict(inp, md, with_video_features=True) for _ in range(4)]
+        torch.cuda.synchronize()
+        for logits, feats in runs:
+            assert torch.equal(logits[0], ref_logits[0])
+            assert torch.equal(feats["video"], ref_feats["video"])
+    # with gradients enabled and trainable decoder parameters the call keeps the autograd path
+    with torch.enable_grad():
+        assert det._single_call_ok(False) == (not any(p.requires_grad for p in det.decoder.parameters()))
+
+
+@pytest.mark.gpu
 def test_full_size_c2_properties(cuda_device):
     """BASELINE config C2 at full size (ViT-B/16, 64 clips x 8 frames): size-independent properties instead of an
     oracle run — clips are independent units (a sub-batch reproduces its rows bit-exactly), reruns are bit-identical,
