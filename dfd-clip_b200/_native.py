@@ -28,6 +28,7 @@ EXPORTS = (
     "dfd_adapter_workspace_bytes", "dfd_adapter_apply", "dfd_ema_frames",
     "dfd_decoder_attention_modes_workspace_bytes", "dfd_decoder_attention_modes",
     "dfd_patchify_u8", "dfd_encoder_forward_u8", "dfd_gemm_bf16_ln", "dfd_predict_forward",
+    "dfd_linear_f32_workspace_bytes", "dfd_linear_f32",
 )
 
 
@@ -132,6 +133,10 @@ def load_library():
                                             c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]
         lib.dfd_project_logits.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                            c_void_p]
+        lib.dfd_linear_f32_workspace_bytes.argtypes = [c_int, c_int]
+        lib.dfd_linear_f32_workspace_bytes.restype = c_size_t
+        lib.dfd_linear_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_int, c_void_p, c_size_t, c_void_p]
         lib.dfd_decoder_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                               c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                               c_size_t, c_void_p]
@@ -273,6 +278,23 @@ def layernorm(x, gamma, beta, pos=None, out_dtype=torch.bfloat16, out=None):
     check(load_library().dfd_layernorm(ctx(x.device), ptr(x), ptr(gamma), ptr(beta), ptr(pos),
                                        0 if pos is None else pos.shape[0], ptr(out) if bf else None,
                                        None if bf else ptr(out), rows, d, stream_ptr(x.device)))
+    return out
+
+
+def linear_f32(x, weight, bias=None, residual=None, quick_gelu=False, out=None):
+    """fp32 ``act(x @ weight.T + bias) + residual`` with the decoder's small-batch linear kernel (x [B,K], weight [N,K])."""
+    assert x.dtype == torch.float32 and weight.dtype == torch.float32 and x.is_contiguous() and weight.is_contiguous()
+    b, k = x.shape
+    n = weight.shape[0]
+    if out is None:
+        out = torch.empty((b, n), dtype=torch.float32, device=x.device)
+    if b == 0:
+        return out
+    lib = load_library()
+    nbytes = lib.dfd_linear_f32_workspace_bytes(b, n)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    check(lib.dfd_linear_f32(ctx(x.device), ptr(x), ptr(weight), ptr(bias), ptr(residual), ptr(out), b, n, k,
+                             1 if quick_gelu else 0, ptr(ws), nbytes, stream_ptr(x.device)))
     return out
 
 

@@ -111,6 +111,11 @@ int decoder_attention(const dfd_ctx* ctx, const float* qs, const void* k, const 
 // stream the K range is split across CTAs: CTA (n-tile of 16 columns, k-split, 64-row b-tile) accumulates a partial
 // [64 x 16] tile with a cp.async double-buffered smem pipeline; partials are reduced in a fixed order by
 // linear_reduce_kernel (deterministic, no atomics), which also applies bias / QuickGELU / residual.
+// Measured and rejected (round 1, profiles/r1d_rejected.md): ONE kernel per linear with 64 x 64 tiles, 8 x 4 register
+// tiles and the split-K reduction done by the last-arriving CTA of a tile (fence + counter) — with 144 CTAs of four
+// warps there is nothing to hide the chain load -> FMA -> store -> fence -> reduce behind: 15-29 us per linear in
+// three variants (row-major smem, k-major smem, whole k-range prefetched) against 13 + 5 us for this pair, whose
+// 384 small CTAs (5 per SM) hide the latencies by occupancy.
 constexpr int LIN_BM = 64, LIN_BN = 16, LIN_BK = 64, LIN_LD = LIN_BK + 4, LIN_THREADS = 128;
 
 __device__ __forceinline__ void cp_async_f4(void* smem_dst, const void* gsrc, bool valid) {
@@ -459,6 +464,25 @@ int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, in
   dfd::clear_error();
   if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_project_logits: ctx is NULL");
   return dfd::project_logits(feature, proj, B, D, O, scale, logits, static_cast<cudaStream_t>(stream));
+}
+
+size_t dfd_linear_f32_workspace_bytes(int B, int N) {
+  if (B <= 0 || N <= 0) return 0;
+  return dfd::linear_workspace_bytes(B, N);
+}
+
+int dfd_linear_f32(dfd_ctx* ctx, const float* x, const float* W, const float* bias, const float* residual, float* out,
+                   int B, int N, int K, int quick_gelu, void* workspace, size_t workspace_bytes, void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_linear_f32: ctx is NULL");
+  if (B < 0 || N <= 0 || K <= 0) return dfd::fail(DFD_ERR_INVALID, "dfd_linear_f32: bad shape B=%d N=%d K=%d", B, N, K);
+  if (B == 0) return 0;
+  if (!x || !W || !out) return dfd::fail(DFD_ERR_INVALID, "dfd_linear_f32: null pointer");
+  if (!workspace || workspace_bytes < dfd::linear_workspace_bytes(B, N))
+    return dfd::fail(DFD_ERR_WORKSPACE, "dfd_linear_f32: workspace %zu < %zu bytes", workspace_bytes,
+                     dfd::linear_workspace_bytes(B, N));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dfd::linear_f32(ctx, x, W, bias, residual, out, B, N, K, quick_gelu != 0, static_cast<float*>(workspace), st);
 }
 
 int dfd_ema_frames(dfd_ctx* ctx, const float* x, float* out, int B, int T, int64_t frame_elems, float ratio,

@@ -241,22 +241,37 @@ def shard_videos(clip_counts, world_size):
 
 
 def video_mean_probs(clip_logits, clip_counts):
-    """softmax per clip, then mean over each video's clips (inference.py:121,140). clip_logits [sum(counts), O]."""
+    """softmax per clip, then mean over each video's clips (inference.py:121,140). clip_logits [sum(counts), O].
+    The per-video sums are accumulated in fp64 over a padded [videos, max_count] gather — no atomics, so the scores are
+    run-to-run deterministic and do not depend on how many videos are reduced in one call (index_add_ on CUDA is
+    neither)."""
     probs = clip_logits.float().softmax(dim=-1)
     counts = torch.as_tensor(list(clip_counts), device=probs.device, dtype=torch.long)
-    video_id = torch.repeat_interleave(torch.arange(len(clip_counts), device=probs.device), counts)
-    sums = torch.zeros((len(clip_counts), probs.shape[1]), dtype=probs.dtype, device=probs.device)
-    sums.index_add_(0, video_id, probs)
-    return sums / counts.clamp_min(1).unsqueeze(1).to(probs.dtype)
+    n_videos = counts.numel()
+    if n_videos == 0:
+        return probs.new_zeros((0, probs.shape[1]))
+    max_count = max(1, int(max(clip_counts)))
+    starts = torch.cumsum(counts, 0) - counts
+    slot = torch.arange(max_count, device=probs.device)
+    valid = slot.unsqueeze(0) < counts.unsqueeze(1)                                   # [V, max_count]
+    index = (starts.unsqueeze(1) + slot.unsqueeze(0)).clamp_(max=max(probs.shape[0] - 1, 0))
+    if probs.shape[0] == 0:
+        return probs.new_zeros((n_videos, probs.shape[1]))
+    padded = probs.double()[index] * valid.unsqueeze(-1)                              # [V, max_count, O]
+    sums = padded.sum(dim=1)
+    return (sums / counts.clamp_min(1).unsqueeze(1)).to(probs.dtype)
 
 
-def pack_clip_batches(videos, masks, batch_clips=64, pin=None):
+def pack_clip_batches(videos, masks, batch_clips=64, pin=None, workers=4):
     """Generator: the clips of ``videos`` (host tensors ``[n_i, T, 3, R, R]``, any mix of lengths, zero allowed) packed
-    in order into batches of ``batch_clips`` clips, video boundaries ignored. Each batch is a view of one of TWO rotating
-    staging buffers (pinned when CUDA is available, so the H2D copy of ``HostClipStream`` is asynchronous) — a consumer
-    may hold a batch only until it asks for the batch after the next one, which is exactly what ``HostClipStream.run``
-    does (batch k-2 has been synchronised before batch k is requested). Nothing is concatenated or pinned up front:
-    host memory beyond the caller's videos is two batches."""
+    in order into batches of ``batch_clips`` clips, video boundaries ignored. Each batch is a view of one of THREE
+    rotating staging buffers (pinned when CUDA is available, so the H2D copy of ``HostClipStream`` is asynchronous);
+    while the consumer works on batch k, a small thread pool already copies batch k+1 into the next buffer (a batch of
+    64 fp32 clips is 308 MB of memcpy: longer than the GPU needs for the previous batch if done by one thread in the
+    consumer's loop). A consumer may hold batch k until it asks for batch k+2, which is exactly what
+    ``HostClipStream.run`` does (batch k-2 has been synchronised before batch k is requested). Nothing is
+    concatenated or pinned up front: host memory beyond the caller's videos is three batches."""
+    from concurrent.futures import ThreadPoolExecutor
     step = max(1, int(batch_clips))
     first = next((v for v in videos if v.shape[0] > 0), None)
     if first is None:
@@ -264,10 +279,9 @@ def pack_clip_batches(videos, masks, batch_clips=64, pin=None):
     if pin is None:
         pin = torch.cuda.is_available()
     m_first = next(m for v, m in zip(videos, masks) if v.shape[0] > 0)
-    stage_x = [torch.empty((step,) + tuple(first.shape[1:]), dtype=first.dtype, pin_memory=pin) for _ in range(2)]
-    stage_m = [torch.empty((step,) + tuple(m_first.shape[1:]), dtype=m_first.dtype, pin_memory=pin) for _ in range(2)]
-    slot, fill = 0, 0
-    for v, m in zip(videos, masks):
+    # plan: per batch, the list of (video index, first clip, clip count, destination row)
+    plan, cur, fill = [], [], 0
+    for i, (v, m) in enumerate(zip(videos, masks)):
         if v.shape[1:] != first.shape[1:] or v.dtype != first.dtype:
             raise ValueError("all videos must share one clip shape and dtype: %s %s vs %s %s" %
                              (tuple(v.shape[1:]), v.dtype, tuple(first.shape[1:]), first.dtype))
@@ -276,15 +290,45 @@ def pack_clip_batches(videos, masks, batch_clips=64, pin=None):
         a, n = 0, int(v.shape[0])
         while a < n:
             take = min(step - fill, n - a)
-            stage_x[slot][fill:fill + take].copy_(v[a:a + take])
-            stage_m[slot][fill:fill + take].copy_(m[a:a + take])
+            cur.append((i, a, take, fill))
             fill += take
             a += take
             if fill == step:
-                yield stage_x[slot], stage_m[slot]
-                slot, fill = 1 - slot, 0
+                plan.append((cur, fill))
+                cur, fill = [], 0
     if fill:
-        yield stage_x[slot][:fill], stage_m[slot][:fill]
+        plan.append((cur, fill))
+    n_slots = min(3, len(plan))
+    stage_x = [torch.empty((step,) + tuple(first.shape[1:]), dtype=first.dtype, pin_memory=pin) for _ in range(n_slots)]
+    stage_m = [torch.empty((step,) + tuple(m_first.shape[1:]), dtype=m_first.dtype, pin_memory=pin)
+               for _ in range(n_slots)]
+    workers = max(1, int(workers))
+    rows_per_task = max(1, -(-step // workers))
+
+    def copy_rows(slot, vid, src, dst, count):
+        stage_x[slot][dst:dst + count].copy_(videos[vid][src:src + count])
+        stage_m[slot][dst:dst + count].copy_(masks[vid][src:src + count])
+
+    pool = ThreadPoolExecutor(max_workers=workers)
+
+    def fill_async(j):
+        futures = []
+        for vid, src, count, dst in plan[j][0]:
+            for off in range(0, count, rows_per_task):
+                c = min(rows_per_task, count - off)
+                futures.append(pool.submit(copy_rows, j % n_slots, vid, src + off, dst + off, c))
+        return futures
+
+    try:
+        pending = fill_async(0)
+        for j in range(len(plan)):
+            for f in pending:
+                f.result()
+            pending = fill_async(j + 1) if j + 1 < len(plan) else []
+            rows = plan[j][1]
+            yield stage_x[j % n_slots][:rows], stage_m[j % n_slots][:rows]
+    finally:
+        pool.shutdown(wait=True)
 
 
 def score_videos_batched(detector, videos, masks, batch_clips=64, group=None):

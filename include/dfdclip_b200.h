@@ -246,6 +246,14 @@ int dfd_predict_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pack
 int dfd_project_logits(dfd_ctx* ctx, const float* feature, const float* proj, int B, int D, int O, float scale,
                        float* logits, void* stream);
 
+/* The decoder's one-token-per-clip nn.Linear layers (src/models.py:69-73, 136, 145: in_proj, out_proj, c_fc, c_proj)
+ * in exact fp32 FMA arithmetic, exported for unit tests: out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]) + residual[b,n],
+ * act = QuickGELU (model.py:166-168) when quick_gelu != 0; bias / residual may be NULL, residual may alias out.
+ * x fp32 [B,K], W fp32 [N,K] (nn.Linear layout), K % 4 == 0. Deterministic (fixed-order split-K reduction). */
+size_t dfd_linear_f32_workspace_bytes(int B, int N);
+int dfd_linear_f32(dfd_ctx* ctx, const float* x, const float* W, const float* bias, const float* residual, float* out,
+                   int B, int N, int K, int quick_gelu, void* workspace, size_t workspace_bytes, void* stream);
+
 /* op_mode.ema_frame (src/models.py:572-578): out[b] = EMA over the T frames of clip b, _x = _x*ratio + x[:, i]*(1-ratio)
  * starting from zero, evaluated in that order in fp32. x fp32 [B, T, frame_elems] -> out fp32 [B, frame_elems];
  * frame_elems % 4 == 0. */

@@ -254,3 +254,33 @@ def test_gemm_lnfold_equals_layernorm_then_linear(cuda_device, m, n, quickgelu):
     err_base = (base - ref).norm() / ref.norm()
     assert err_fold.item() < 1.5e-2, err_fold
     assert err_fold.item() < 3 * err_base.item() + 4e-3, (err_fold, err_base)
+
+
+@pytest.mark.parametrize("b,n,k", [(64, 1536, 768), (64, 768, 3072), (1, 768, 768), (3, 100, 36), (65, 3072, 768),
+                                   (130, 2, 768), (12, 1024, 4096), (7, 250, 1000)])
+@pytest.mark.parametrize("mode", ["plain", "bias", "bias_gelu", "bias_residual_in_place"])
+def test_linear_f32(cuda_device, b, n, k, mode):
+    """The decoder's one-token-per-clip linear (src/models.py:136, 145, 69-73) in exact fp32 arithmetic: every split-K
+    configuration, ragged tiles in all three dimensions, bias / QuickGELU / in-place residual epilogues, against an
+    fp64 reference; run twice for bit-exact determinism (the last-arriving CTA reduces in a fixed order)."""
+    from dfdclip_b200 import _native as nat
+    g = torch.Generator().manual_seed(b * 7 + n * 3 + k)
+    x = torch.randn((b, k), generator=g).to(cuda_device)
+    w = (torch.randn((n, k), generator=g) * k ** -0.5).to(cuda_device)
+    bias = torch.randn((n,), generator=g).to(cuda_device) if mode != "plain" else None
+    res = torch.randn((b, n), generator=g).to(cuda_device) if mode == "bias_residual_in_place" else None
+    ref = x.double() @ w.double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if mode == "bias_gelu":
+        ref = ref * torch.sigmoid(1.702 * ref)
+    if res is not None:
+        ref = ref + res.double()
+    outs = []
+    for _ in range(2):
+        out = res.clone() if res is not None else None
+        got = nat.linear_f32(x, w, bias, out, quick_gelu=(mode == "bias_gelu"), out=out)
+        outs.append(got.clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0].double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())

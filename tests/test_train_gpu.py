@@ -241,3 +241,64 @@ def test_train_modes_the_reference_cannot_run_raise():
         cfg.train_mode[key] = val
         with pytest.raises(NotImplementedError):
             Detector(cfg, 4, None)
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_graphed_train_step_matches_eager_steps(cuda_device, u8):
+    """GraphedTrainStep (forward(train=True) + backward + SGD step captured once, replayed per batch) against the same
+    three steps run eagerly on an identical detector: losses, logits and every trained parameter agree, constructing the
+    step does not change the weights, and a batch of another shape is refused."""
+    import copy
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.models import Detector
+    from dfdclip_b200.training import GraphedTrainStep
+    arch, frames, clips = "small-512x6", 3, 4
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:" + arch
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    det_a = Detector(cfg, frames, None)
+    sd = synthetic.detector_state_dict(arch, frames, out_dims=(2,), taps=det_a.layer_indices, seed=0)
+    det_a.load_state_dict(sd, strict=True)
+    det_b = copy.deepcopy(det_a)
+    det_a, det_b = det_a.to(cuda_device).train(), det_b.to(cuda_device).train()
+    res = synthetic.vit_dims(arch)["image_size"]
+    batches = []
+    for i in range(3):
+        x, m = synthetic.make_clips(clips, frames, res, seed=60 + i)
+        if u8:
+            x = torch.randint(0, 256, tuple(x.shape), generator=torch.Generator().manual_seed(80 + i), dtype=torch.uint8)
+        y = torch.randint(0, 2, (clips,), generator=torch.Generator().manual_seed(70 + i))
+        batches.append((x.to(cuda_device), y.to(cuda_device), m.to(cuda_device)))
+
+    opt_a = det_a.configure_optimizers(lr=0.05)
+    eager = []
+    for x, y, m in batches:
+        with torch.enable_grad():
+            losses, logits, _ = det_a(x, [y], m, train=True, single_task=0)
+            loss = losses[0].mean()
+            loss.backward()
+        opt_a.step()
+        opt_a.zero_grad(set_to_none=True)
+        eager.append((loss.item(), logits[0].detach().clone()))
+
+    opt_b = det_b.configure_optimizers(lr=0.05)
+    before = [p.detach().clone() for p in det_b.parameters()]
+    step = GraphedTrainStep(det_b, opt_b, *batches[2])  # example batch: any batch of the right shape
+    torch.cuda.synchronize()
+    assert all(torch.equal(p, q) for p, q in zip(det_b.parameters(), before))
+    for (x, y, m), (ref_loss, ref_logits) in zip(batches, eager):
+        loss, logits = step(x, y, m)
+        assert abs(loss.item() - ref_loss) < 1e-4
+        assert (logits - ref_logits).abs().max().item() < 1e-3
+    moved = 0
+    for (name, p), q, p0 in zip(det_b.named_parameters(), det_a.parameters(), before):
+        if not p.requires_grad:
+            assert torch.equal(p, p0), name
+            continue
+        delta = (q - p0).norm().item()
+        assert (p - q).norm().item() <= 1e-3 * delta + 1e-6, (name, (p - q).norm().item(), delta)
+        moved += delta > 0
+    assert moved >= 30
+    with pytest.raises(ValueError):
+        step(batches[0][0][:2], batches[0][1][:2], batches[0][2][:2])
