@@ -215,7 +215,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- b200 arm
@@ -423,10 +423,30 @@ def run_b200(args, rank, world, local_rank):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, written to the process's ORIGINAL stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    # stdout carries exactly one JSON line. Libraries write there too (NCCL prints its version banner to stdout under
+    # NCCL_DEBUG=WARN, which the GPU boxes set), so file descriptor 1 is pointed at stderr for the whole run and the
+    # result goes to a private duplicate of the original stdout.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

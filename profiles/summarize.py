@@ -20,10 +20,14 @@ def short(name):
     return name.replace("void ", "").replace("dfd::", "")
 
 
-def launches(src, dst, skip_pack=True):
+def launches(src, dst, skip_pack=True, last_predicts=0):
     rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
     hdr = rows[0]
     ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
+    if last_predicts:
+        # a predict starts with the patch extraction kernel: keep the last N whole predicts of the run
+        starts = [i for i, r in enumerate(rows) if i > 0 and "patchify_kernel" in r[ki]]
+        rows = [hdr] + rows[starts[-last_predicts]:]
     agg = OrderedDict()
     for r in rows[1:]:
         k = short(r[ki])
@@ -91,5 +95,7 @@ if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif mode == "launches_last":  # launches_last N src.csv dst.md: only the last N predicts of the run
+        launches(sys.argv[3], sys.argv[4], last_predicts=int(sys.argv[2]))
     else:
         raw(sys.argv[2:-1], sys.argv[-1])
