@@ -15,7 +15,9 @@ OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libdfdclip_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-NVCC_FLAGS = (["-DDFD_MHA_TRACE"] if os.environ.get("DFD_MHA_TRACE") else []) + [
+# DFD_NVCC_EXTRA: extra compiler flags for experiments (e.g. "-DDFD_EXP2_POLY_NUM=1 -DDFD_EXP2_POLY_DEN=4")
+NVCC_FLAGS = (["-DDFD_MHA_TRACE"] if os.environ.get("DFD_MHA_TRACE") else []) + \
+    os.environ.get("DFD_NVCC_EXTRA", "").split() + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -111,6 +111,15 @@ __device__ __forceinline__ void ld_chunk(uint32_t t_s, int c, uint32_t (&r)[32])
   }
 }
 
+// e[j] = 2^(s_j * sc - mo) for j < w (w = 32 or 16), element j on the pipe softmax_exp2<j> selects
+template <int J>
+__device__ __forceinline__ void exp2_chunk(float (&e)[32], const uint32_t (&cur)[32], float sc, float mo, int w) {
+  if constexpr (J < 32) {
+    if (J < 16 || w == 32) e[J] = softmax_exp2<J>(fmaf(__uint_as_float(cur[J]), sc, -mo));
+    exp2_chunk<J + 1>(e, cur, sc, mo, w);
+  }
+}
+
 __global__ void __launch_bounds__(attn2::THREADS, 1)
 mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmO, int L, int H, int num_items) {
@@ -299,8 +308,7 @@ mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (c + 1 < NCHUNK) ld_chunk(t_row, c + 1, nx);
             const int c0 = c * 32, w = (c < 6) ? 32 : 16;
             if (c < 4 || c0 + w <= L) {
-#pragma unroll
-              for (int j = 0; j < w; ++j) e[j] = fast_exp2(fmaf(__uint_as_float(cur[j]), sc, -mo));
+              exp2_chunk<0>(e, cur, sc, mo, w);
             } else {
 #pragma unroll
               for (int j = 0; j < w; ++j)

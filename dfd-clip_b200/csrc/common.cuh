@@ -213,6 +213,39 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x for x <= ~0 on the FMA / integer pipes instead of the MUFU (XU) pipe: round-to-nearest range reduction with
+// the 1.5 * 2^23 trick, a cubic for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding the
+// softmax weights get next), exponent added as an integer. The attention kernels give a fixed share of each row's
+// exponentials to this routine so that both pipes work on the softmax at once (the exp2 pass is the longest link of
+// the per-item chain and MUFU issues only 4 lanes per clock per sub-partition).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;        // integer part in the low mantissa bits
+  const float f = x - (t - 12582912.f);  // [-0.5, 0.5]
+  float p = fmaf(0.0551716648f, f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// DFD_EXP2_POLY_NUM of every DFD_EXP2_POLY_DEN exponentials of a softmax row go to poly_exp2 (0 = all on MUFU).
+// Measured on the ViT-B/16 attention kernel (B200, C2 shape, 50 launches): 0/1 151.7 us, 1/4 155.7, 1/3 184.6,
+// 1/2 235.2, 2/3 312.3 — with one softmax warp per sub-partition the exp2 pass is bound by instruction issue, not by
+// the MUFU pipe, so the nine instructions of the polynomial cost more than the MUFU cycles they free. Default: off.
+#ifndef DFD_EXP2_POLY_NUM
+#define DFD_EXP2_POLY_NUM 0
+#endif
+#ifndef DFD_EXP2_POLY_DEN
+#define DFD_EXP2_POLY_DEN 2
+#endif
+template <int J>
+__device__ __forceinline__ float softmax_exp2(float x) {
+  if constexpr ((J % DFD_EXP2_POLY_DEN) < DFD_EXP2_POLY_NUM)
+    return poly_exp2(x);
+  else
+    return fast_exp2(x);
+}
+
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             uint64_t hint) {
   asm volatile(
