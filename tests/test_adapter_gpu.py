@@ -158,6 +158,15 @@ def test_adapter_against_oracle_with_masks_and_host_pipeline(cuda_device):
     assert torch.equal(again[0], logits[0])  # deterministic; the taps of a call are adapted exactly once
     pipe = HostClipPipeline(det, chunk_clips=4)
     assert torch.equal(pipe(x.pin_memory(), m.pin_memory()), logits[0].cpu())
+    # the cross-batch stream (adapter applied per batch on that batch's own tap buffers, decoder on its own stream)
+    from dfdclip_b200.inference import HostClipStream
+    xp, mp = x.pin_memory(), m.pin_memory()
+    for overlap in (True, False):
+        stream = HostClipStream(det, overlap_decoder=overlap)
+        got = torch.cat(list(stream.run([(xp[:4], mp[:4]), (xp[4:], mp[4:]), (xp[:4], mp[:4])])))
+        want = torch.cat([det.predict(xp[a:b_].to(cuda_device), mp[a:b_].to(cuda_device))[0][0].cpu()
+                          for a, b_ in ((0, 4), (4, 9), (0, 4))])
+        assert torch.equal(got, want)
 
 
 def test_frozen_adapter_trains_decoder_only(cuda_device):
