@@ -95,6 +95,23 @@ int dfd_ctx_create(int device, dfd_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   c->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   c->encode_tiled = fn;
+  // side stream + fork/join/tap events of dfd_predict_forward: created here, not on first use, so that a first
+  // predict inside a CUDA-graph capture creates nothing (highest priority: the decoder's small kernels are placed as
+  // soon as SMs free up)
+  int lo = 0, hi = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork_event, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join_event, cudaEventDisableTiming);
+  for (int i = 0; i < 64 && e == cudaSuccess; ++i) {
+    cudaEvent_t ev;
+    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) c->tap_events.push_back(ev);
+  }
+  if (e != cudaSuccess) {
+    dfd_ctx_destroy(c);
+    return dfd::fail(DFD_ERR_CUDA, "dfd_ctx_create: stream/event creation failed: %s", cudaGetErrorString(e));
+  }
   *out = c;
   return 0;
 }
