@@ -15,7 +15,7 @@ c_void_p, c_int, c_int64, c_size_t, c_float = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float)
 
 EPI_STORE_BF16, EPI_STORE_BF16_QGELU, EPI_STORE_F32, EPI_ADD_F32, EPI_ADD_BF16, EPI_STORE_BF16_GELU = 0, 1, 2, 3, 4, 5
-ADAPTER_GELU_LN, ADAPTER_LN_GELU, ADAPTER_NLN, ADAPTER_XXX, ADAPTER_LINEAR = 0, 1, 2, 3, 4
+ADAPTER_GELU_LN, ADAPTER_LN_GELU, ADAPTER_NLN, ADAPTER_XXX, ADAPTER_LINEAR, ADAPTER_BN = 0, 1, 2, 3, 4, 5
 
 # Every symbol include/dfdclip_b200.h declares (tests check the library exports each of them).
 EXPORTS = (

@@ -158,9 +158,34 @@ static int launch_rownorm(void* h, const float* g, const float* b, int64_t rows,
   return 0;
 }
 
+// "768-bn": kv[row, :] += scale[f] * h[row, :] + shift[f], f = row / group_rows. One thread per 8 channels.
+__global__ void __launch_bounds__(256)
+adapter_frame_affine_kernel(__nv_bfloat16* __restrict__ kv, int64_t ld, const __nv_bfloat16* __restrict__ h,
+                            const float* __restrict__ scale, const float* __restrict__ shift, int64_t rows, int D,
+                            int group_rows) {
+  const int vec_per_row = D / 8;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * vec_per_row) return;
+  const int64_t row = i / vec_per_row;
+  const int c = static_cast<int>(i % vec_per_row) * 8;
+  const int64_t f = row / group_rows;
+  const float sc = scale[f], sh = shift[f];
+  uint4 a = *reinterpret_cast<const uint4*>(kv + row * ld + c);
+  const uint4 b = *reinterpret_cast<const uint4*>(h + row * D + c);
+  uint32_t* aw = reinterpret_cast<uint32_t*>(&a);
+  const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a0 = __uint_as_float(aw[j] << 16), a1 = __uint_as_float(aw[j] & 0xffff0000u);
+    const float b0 = __uint_as_float(bw[j] << 16), b1 = __uint_as_float(bw[j] & 0xffff0000u);
+    aw[j] = pack_bf16(a0 + fmaf(sc, b0, sh), a1 + fmaf(sc, b1, sh));
+  }
+  *reinterpret_cast<uint4*>(kv + row * ld + c) = a;
+}
+
 static size_t adapter_ws(int type, int D, int inner, int64_t rows) {
   const size_t r = static_cast<size_t>(rows);
-  if (type == DFD_ADAPTER_LINEAR) return r * D * 2;
+  if (type == DFD_ADAPTER_LINEAR || type == DFD_ADAPTER_BN) return r * D * 2;
   return r * inner * 2 * (type == DFD_ADAPTER_XXX ? 2 : 1);
 }
 
@@ -168,11 +193,11 @@ int adapter_apply(const dfd_ctx* ctx, int type, int D, int inner, const dfd_adap
                   int64_t rows, int group_rows, int group_skip, void* workspace, size_t ws_bytes,
                   cudaStream_t stream) {
   DFD_CHECK_ARG(w && kv, "adapter: null pointer");
-  DFD_CHECK_ARG(type >= DFD_ADAPTER_GELU_LN && type <= DFD_ADAPTER_LINEAR, "adapter: unknown struct type %d", type);
+  DFD_CHECK_ARG(type >= DFD_ADAPTER_GELU_LN && type <= DFD_ADAPTER_BN, "adapter: unknown struct type %d", type);
   DFD_CHECK_ARG(D > 0 && D % 256 == 0, "adapter: width %d must be a multiple of 256", D);
   DFD_CHECK_ARG(rows >= 0 && rows < (1ll << 31) - 256, "adapter: row count out of range");
   if (rows == 0) return 0;
-  if (type == DFD_ADAPTER_LINEAR) inner = D;
+  if (type == DFD_ADAPTER_LINEAR || type == DFD_ADAPTER_BN) inner = D;
   DFD_CHECK_ARG(inner > 0 && inner % 256 == 0 && inner <= 1024, "adapter: inner width %d must be 256, 512, 768 or 1024",
                 inner);
   const size_t need = adapter_ws(type, D, inner, rows);
@@ -189,6 +214,21 @@ int adapter_apply(const dfd_ctx* ctx, int type, int D, int inner, const dfd_adap
     DFD_CUDA_OK(cudaMemcpy2DAsync(kv, static_cast<size_t>(ld) * 2, workspace, static_cast<size_t>(D) * 2,
                                   static_cast<size_t>(D) * 2, static_cast<size_t>(rows), cudaMemcpyDeviceToDevice,
                                   stream));
+    return 0;
+  }
+  if (type == DFD_ADAPTER_BN) {
+    // tap += BatchNorm2d_eval(Linear(D, D)(tap)) (src/models.py:877-887, 930-931): the normalisation is one scalar
+    // affine per frame, applied while the product is added to the tap
+    DFD_CHECK_ARG(w->ln_weight && w->ln_bias, "adapter: missing per-frame scale / shift");
+    DFD_CHECK_ARG(group_rows > 0 && rows % group_rows == 0, "adapter: %lld rows are not whole frames of %d rows",
+                  (long long)rows, group_rows);
+    DFD_CHECK_ARG(ld % 8 == 0 && reinterpret_cast<uintptr_t>(kv) % 16 == 0, "adapter: tap must be 16-byte aligned");
+    DFD_TRY(gemm_bf16(ctx, kv, ld, w->w_down, D, nullptr, workspace, D, M, D, D, DFD_EPI_STORE_BF16, stream));
+    const int64_t vecs = rows * (D / 8);
+    adapter_frame_affine_kernel<<<static_cast<unsigned>((vecs + 255) / 256), 256, 0, stream>>>(
+        static_cast<__nv_bfloat16*>(kv), ld, static_cast<const __nv_bfloat16*>(workspace), w->ln_weight, w->ln_bias,
+        rows, D, group_rows);
+    DFD_CUDA_OK(cudaGetLastError());
     return 0;
   }
   DFD_CHECK_ARG(w->w_up != nullptr, "adapter: missing up-projection weight");
@@ -225,7 +265,7 @@ int adapter_apply(const dfd_ctx* ctx, int type, int D, int inner, const dfd_adap
 
 extern "C" size_t dfd_adapter_workspace_bytes(int type, int D, int inner, int64_t rows) {
   if (rows <= 0 || D <= 0) return 0;
-  return dfd::adapter_ws(type, D, type == DFD_ADAPTER_LINEAR ? D : inner, rows);
+  return dfd::adapter_ws(type, D, (type == DFD_ADAPTER_LINEAR || type == DFD_ADAPTER_BN) ? D : inner, rows);
 }
 
 extern "C" int dfd_adapter_apply(dfd_ctx* ctx, int type, int D, int inner, const dfd_adapter_weights* w, void* kv,

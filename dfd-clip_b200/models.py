@@ -4,9 +4,9 @@
 
 Supported: the CLIP foundation with stride or index taps; every ``op_mode`` switch of the reference
 (``temporal_position``, ``aug_query``, ``global_prediction``, ``ema_frame``, ``attn_mode``); ``train_mode.patch_mask``
-and ``train_mode.temporal``; dropout; the ``CompInvAdapter`` (:783-940) with every struct but ``768-bn`` — natively
+and ``train_mode.temporal``; dropout; the ``CompInvAdapter`` (:783-940) with every struct — natively
 in place on the taps in inference or when frozen, under autograd (with native dK/dV from the decoder attention) when
-trained. What is not implemented (``foundation: dinov2``, ``768-bn``, and ``train_mode.compression`` / ``nerf_raw``,
+trained. What is not implemented (``foundation: dinov2`` and ``train_mode.compression`` / ``nerf_raw``,
 which the reference itself cannot execute) raises ``NotImplementedError`` instead of silently diverging. There is no
 CPU / PyTorch fallback for the encoder, the adapter's inference path or the decoder attention.
 """
@@ -402,6 +402,7 @@ class CompInvAdapter(nn.Module):
         "768-x-768-z0": _native.ADAPTER_LN_GELU,
         "768-xxx-768": _native.ADAPTER_XXX,
         "linear": _native.ADAPTER_LINEAR,
+        "768-bn": _native.ADAPTER_BN,
     }
 
     def __init__(self, config, detector, num_frames=50):
@@ -409,15 +410,13 @@ class CompInvAdapter(nn.Module):
         width = detector.encoder.width
         patches = (detector.encoder.input_resolution // detector.encoder.patch_size) ** 2
         kind = config.adapter.struct.type
-        if kind == "768-bn":
-            raise NotImplementedError("adapter.struct.type='768-bn' (BatchNorm2d over frames) is not implemented "
-                                      "by the B200 path")
         if kind not in self._STRUCTS:
             raise NotImplementedError("unknown adapter.struct.type %r" % (kind,))
         self.struct_type = kind
         self.kind = self._STRUCTS[kind]
         self.width, self.patches = width, patches
-        self.inner = width if kind == "linear" else int(config.adapter.struct.x)
+        self.inner = width if kind in ("linear", "768-bn") else int(config.adapter.struct.x)
+        self.num_frames = int(num_frames)
         if self.inner % 256 != 0 or self.inner > 1024:
             raise NotImplementedError("adapter.struct.x=%d: the B200 path needs 256, 512, 768 or 1024" % self.inner)
         self.residual = kind != "linear"
@@ -446,6 +445,10 @@ class CompInvAdapter(nn.Module):
                     mod = nn.Sequential(nn.Linear(width, x, bias=False), nn.GELU(), nn.Dropout(p / 5),
                                         nn.Linear(x, x, bias=False), nn.GELU(), nn.Dropout(p / 5),
                                         nn.Linear(x, width, bias=False), nn.Dropout(p))
+                elif kind == "768-bn":
+                    # BatchNorm2d over [b, t, p, width]: the frame index is the channel (reference :877-887, which
+                    # hard-codes Linear(768, 768); the encoder width is used here, identical for ViT-B)
+                    mod = nn.Sequential(nn.Linear(width, width, bias=False), nn.BatchNorm2d(num_frames), nn.Dropout(p))
                 else:  # "linear"
                     mod = nn.Sequential(nn.Linear(width, width, bias=False), nn.Dropout(p))
                     mod[0].weight.data = torch.eye(width)
@@ -460,7 +463,7 @@ class CompInvAdapter(nn.Module):
         """True when the call must go through ``forward_autograd``: the adapter is being trained (parameters require
         grad and grad mode is on) or its dropout layers are active."""
         return (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())) or \
-            (self.training and self.dropout > 0)
+            (self.training and (self.dropout > 0 or self.kind == _native.ADAPTER_BN))  # train-mode BN: batch statistics
 
     def _check_mode(self):
         if self.needs_autograd():
@@ -505,9 +508,27 @@ class CompInvAdapter(nn.Module):
                 raise _native.NativeError("adapter LayerNorm parameters must be contiguous fp32 tensors")
         return w_down, w_mid, w_up, ln_w, ln_b
 
+    def _frame_affine(self, bn, frames):
+        """Eval-mode BatchNorm2d(num_frames) as one (scale, shift) pair per frame of the batch: frame f of a clip uses
+        channel f (reference :877-887 on [b, t, p, width]); fp32 device vectors of length ``frames``."""
+        t = bn.num_features
+        if frames % t != 0:
+            raise ValueError("the 768-bn adapter was built for clips of %d frames; got %d frames in the batch" %
+                             (t, frames))
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        shift = bn.bias.detach().float() - bn.running_mean.float() * scale
+        return scale.repeat(frames // t).contiguous(), shift.repeat(frames // t).contiguous()
+
     def _adapt(self, mod, tap, rows, ld, group_rows, group_skip):
         if tap.device.type != "cuda":
             raise _native.NativeError("dfdclip_b200 adapter needs CUDA tensors (no CPU fallback)")
+        if self.kind == _native.ADAPTER_BN:
+            scale, shift = self._frame_affine(mod[1], rows // group_rows)
+            with torch.cuda.device(tap.device):
+                self._workspace = _native.adapter_apply(self.kind, tap, rows, ld, self.width, self.inner,
+                                                        self._gemm_weight(mod[0]), None, None, scale, shift,
+                                                        group_rows, group_skip, self._workspace)
+            return
         w_down, w_mid, w_up, ln_w, ln_b = self._native_args(mod)
         with torch.cuda.device(tap.device):
             self._workspace = _native.adapter_apply(self.kind, tap, rows, ld, self.width, self.inner, w_down, w_mid,

@@ -162,7 +162,7 @@ ADAPTER_LAYOUT = {
 }
 
 
-def adapter_state_dict(arch, n_taps, struct_type, inner=256, seed=0):
+def adapter_state_dict(arch, n_taps, struct_type, inner=256, seed=0, num_frames=None):
     """fp32 state dict of a ``CompInvAdapter`` (keys ``l{i}_{k|v}.{idx}.{weight|bias}``, src/models.py:783-919) with
     random, non-degenerate weights. The up-projection is scaled so that the adapter's contribution is about a
     quarter of the tap it is added to: the shipped structs start from the identity ("-z0", :856-858) and learn a
@@ -172,8 +172,22 @@ def adapter_state_dict(arch, n_taps, struct_type, inner=256, seed=0):
     d = vit_dims(arch)
     w = d["width"]
     patches = (d["image_size"] // d["patch_size"]) ** 2
-    first, ln, mid, last = ADAPTER_LAYOUT[struct_type]
     sd = OrderedDict()
+    if struct_type == "768-bn":
+        # Linear(w, w, bias=False) -> BatchNorm2d(num_frames) over [b, t, p, w] (channel = frame index, :877-887):
+        # non-trivial affine and running statistics so that the eval-mode normalisation is exercised
+        assert num_frames is not None, "the 768-bn struct needs num_frames"
+        for i in range(n_taps):
+            for j in ("k", "v"):
+                pre = "l%d_%s." % (i, j)
+                sd[pre + "0.weight"] = _randn(seed, "ad." + pre + "bn.lin", (w, w), 0.25 * w ** -0.5)
+                sd[pre + "1.weight"] = _randn(seed, "ad." + pre + "bn.w", (num_frames,), 0.1, 1.0)
+                sd[pre + "1.bias"] = _randn(seed, "ad." + pre + "bn.b", (num_frames,), 0.05)
+                sd[pre + "1.running_mean"] = _randn(seed, "ad." + pre + "bn.rm", (num_frames,), 0.05)
+                sd[pre + "1.running_var"] = _randn(seed, "ad." + pre + "bn.rv", (num_frames,), 0.1, 1.0).abs() + 0.1
+                sd[pre + "1.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+        return sd
+    first, ln, mid, last = ADAPTER_LAYOUT[struct_type]
     for i in range(n_taps):
         for j in ("k", "v"):
             pre = "l%d_%s." % (i, j)
@@ -205,7 +219,7 @@ def detector_state_dict(arch, num_frames, out_dims=(2,), taps=None, seed=0, adap
         sd["ranking_transform_param"] = _randn(seed, "ranking_transform_param", (w, 1), w ** -0.5)
     if adapter is not None:
         n_taps = len(layer_indices(arch) if taps is None else list(taps))
-        for k, v in adapter_state_dict(arch, n_taps, adapter, adapter_inner, seed).items():
+        for k, v in adapter_state_dict(arch, n_taps, adapter, adapter_inner, seed, num_frames=num_frames).items():
             sd["adapter." + k] = v
     return sd
 

@@ -284,7 +284,11 @@ enum {
   DFD_ADAPTER_LN_GELU = 1, /* "768-x-768-ln", "768-x-768-z0":  Linear, LayerNorm(x), GELU, Linear   (:835-861) */
   DFD_ADAPTER_NLN = 2,     /* "768-x-768-nln": Linear, LayerNorm((patches, x)), GELU, Linear        (:819-834) */
   DFD_ADAPTER_XXX = 3,     /* "768-xxx-768":   Linear, GELU, Linear, GELU, Linear                   (:881-899) */
-  DFD_ADAPTER_LINEAR = 4   /* "linear":        Linear(D, D), no residual                            (:900-917) */
+  DFD_ADAPTER_LINEAR = 4,  /* "linear":        Linear(D, D), no residual                            (:900-917) */
+  DFD_ADAPTER_BN = 5       /* "768-bn":        Linear(D, D), BatchNorm2d(num_frames) in eval mode   (:877-887):
+                            * kv += scale[f] * (kv . W^T) + shift[f], f = frame of the row; ln_weight / ln_bias carry
+                            * fp32 [rows / group_rows] per-frame scale = gamma / sqrt(running_var + eps) and
+                            * shift = beta - running_mean * scale (the frame's position in its clip picks the channel) */
 };
 
 typedef struct {

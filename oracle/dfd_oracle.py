@@ -157,8 +157,24 @@ _ADAPTER_LAYOUT = {
 def adapter_forward(sd, kvs, struct_type, prefix="adapter."):
     """CompInvAdapter.forward (src/models.py:921-935) in eval mode (every Dropout is the identity) for the
     Sequential layouts of :797-917. kvs: list of {k, v: [B,T,P,H,dh]}; returns the adapted list (new tensors)."""
-    first, ln, mid, last = _ADAPTER_LAYOUT[struct_type]
     b, t, p, h, d = kvs[0]["k"].shape
+    if struct_type == "768-bn":
+        # Linear(768, 768, bias=False) -> BatchNorm2d(num_frames) in eval mode (:877-887): dim 1 of [b, t, p, 768] is
+        # the BatchNorm channel, i.e. one scalar affine per frame index from the running statistics (eps 1e-5)
+        out = []
+        for i, kv in enumerate(kvs):
+            new = {}
+            for name in ("k", "v"):
+                pre = "%sl%d_%s." % (prefix, i, name)
+                x = kv[name].float().reshape(b, t, p, h * d)
+                y = F.linear(x, sd[pre + "0.weight"])
+                scale = sd[pre + "1.weight"] / torch.sqrt(sd[pre + "1.running_var"] + 1e-5)
+                shift = sd[pre + "1.bias"] - sd[pre + "1.running_mean"] * scale
+                y = y * scale.view(1, t, 1, 1) + shift.view(1, t, 1, 1)
+                new[name] = kv[name].float() + y.view(b, t, p, h, d)     # :930-931
+            out.append(new)
+        return out
+    first, ln, mid, last = _ADAPTER_LAYOUT[struct_type]
     out = []
     for i, kv in enumerate(kvs):
         new = {}

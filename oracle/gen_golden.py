@@ -45,6 +45,7 @@ CASES = {
     "tiny_ad_linear": ("tiny-256x4", 4, 3, True, "linear"),
     "vitb16_ad_nln": ("ViT-B/16", 8, 2, False, "768-x-768-nln"),
     "vitb16_ad_z0": ("ViT-B/16", 8, 2, False, "768-x-768-z0"),
+    "vitb16_ad_bn": ("ViT-B/16", 8, 2, False, "768-bn"),  # the reference hard-codes Linear(768, 768): width 768 only
     # non-default decoder modes (src/models.py:107-115, 250-267, 345-357, 511-544, 572-578)
     "tiny_aug_query": ("tiny-256x4", 4, 3, True, None, {"aug_query": 1}),
     "tiny_global_pred": ("tiny-256x4", 4, 3, True, None, {"global_prediction": 1}),

@@ -45,7 +45,7 @@ def check_labels(got, ref, margin=4 * TOL_LOGIT_ABS):
 
 
 @pytest.mark.parametrize("case", ["tiny_ad_x", "tiny_ad_legacy", "tiny_ad_nln", "tiny_ad_ln", "tiny_ad_z0",
-                                  "tiny_ad_xxx", "tiny_ad_linear", "vitb16_ad_nln", "vitb16_ad_z0"])
+                                  "tiny_ad_xxx", "tiny_ad_linear", "vitb16_ad_nln", "vitb16_ad_z0", "vitb16_ad_bn"])
 def test_adapter_predict_matches_reference_golden(cuda_device, case):
     g = load_golden(case)
     sd, x, m = golden_inputs(g)
@@ -212,3 +212,32 @@ def test_shipped_config_shape_against_oracle(cuda_device):
     assert np.abs(got - ref).max() <= TOL_LOGIT_ABS, np.abs(got - ref).max()
     check_labels(got, ref)
     assert cosine(feats["video"].cpu(), ref_feat) >= TOL_FEATURE_COSINE
+
+
+def test_bn_adapter_eval_is_native_and_train_mode_uses_batch_statistics(cuda_device):
+    """adapter.struct.type = "768-bn" (reference :877-887): in eval mode the native path applies the running statistics
+    as one affine per frame index (checked against the oracle at a width the reference's hard-coded Linear(768, 768)
+    cannot take); in train mode BatchNorm normalises with batch statistics, so the call must leave the native in-place
+    path for the torch modules, and its running statistics move."""
+    from dfdclip_b200 import synthetic
+    oracle = load_oracle()
+    arch, t, b = "small-512x6", 3, 4
+    det, sd = build_adapter_detector(arch, t, "768-bn", cuda_device)
+    assert any(k.endswith("l0_k.1.running_var") for k in det.state_dict())
+    x, m = synthetic.make_clips(b, t, synthetic.vit_dims(arch)["image_size"], seed=17)
+    with torch.no_grad():
+        ref_logits, _ = oracle.detector_predict(sd, x, m, det.layer_indices, (2,), adapter="768-bn")
+    assert not det.adapter.needs_autograd()
+    logits, _ = det.predict(x.to(cuda_device), m.to(cuda_device))
+    got, ref = logits[0].cpu().numpy(), ref_logits[0].numpy()
+    assert np.abs(got - ref).max() <= TOL_LOGIT_ABS
+    check_labels(got, ref)
+    with pytest.raises(ValueError):  # a batch whose frame count is not a multiple of the BatchNorm's channels
+        det.adapter.apply_packed(det.encoder.encode(x[:1, :2].flatten(0, 1).to(cuda_device),
+                                                    keep_layers=det.layer_indices)[0], det.layer_indices, 2,
+                                 det.encoder.tokens_per_frame)
+    det.train()
+    assert det.adapter.needs_autograd()
+    before = det.adapter.l0_k[1].running_mean.clone()
+    det.predict(x.to(cuda_device), m.to(cuda_device))
+    assert not torch.equal(det.adapter.l0_k[1].running_mean, before)

@@ -115,7 +115,7 @@ def test_index_decode_mode_and_unsupported_knobs():
                    lambda c: c.op_mode.__setitem__("ema_frame", 0.3),  # needs temporal_position = 0
                    lambda c: c.adapter.__setitem__("type", "lora"),
                    lambda c: (c.adapter.__setitem__("type", "normal"),
-                              c.adapter.__setitem__("struct", CN({"type": "768-bn", "x": 256}))),
+                              c.adapter.__setitem__("struct", CN({"type": "768-cn", "x": 256}))),
                    lambda c: (c.adapter.__setitem__("type", "normal"),
                               c.adapter.__setitem__("struct", CN({"type": "768-x-768-z0", "x": 100}))),
                    lambda c: c.__setitem__("foundation", "dinov2"),

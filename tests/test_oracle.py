@@ -36,7 +36,7 @@ def test_oracle_matches_reference_golden(oracle, case):
 
 
 ADAPTER_CASES = ["tiny_ad_x", "tiny_ad_legacy", "tiny_ad_nln", "tiny_ad_ln", "tiny_ad_z0", "tiny_ad_xxx",
-                 "tiny_ad_linear", "vitb16_ad_nln", "vitb16_ad_z0"]
+                 "tiny_ad_linear", "vitb16_ad_nln", "vitb16_ad_z0", "vitb16_ad_bn"]
 
 
 @pytest.mark.parametrize("case", ADAPTER_CASES)
