@@ -8,6 +8,14 @@ One "step" = one pass of the hot path over one batch of synthetic clips per GPU 
 x 224^2, ViT-B/16, taps [0,2,..,10], bf16 tensor-core math / fp32 accumulate). Under torchrun every rank runs the
 same per-GPU batch (weak scaling, clips are independent units) and the per-clip scores are all-gathered once
 per step (the "final logit/score gather" of inference.py:147). Prints ONE JSON line on rank 0.
+
+Keys beyond the base contract: `value` is device-resident (inputs in HBM when the timed region starts); `e2e` is the
+same metric through the public caller loop `dfdclip_b200.inference.predict_stream` with pinned HOST clips in and
+host logits out (H2D / encoder / decoder + D2H of consecutive batches on three streams; every batch's copies inside
+the timed region); `e2e_u8` the same on raw uint8 pixels; `e2e_single_call` one blocking host call per batch;
+`roofline` for the dominant kernel family (tcgen05 GEMMs; per-launch CUDA events in a separate pass, peak from
+MEASURED_PEAKS.json) plus `hbm_kernels`; `cpu_baseline` = the oracle port on the host cores (N=1 only);
+`--impl reference` times that CPU path alone.
 """
 import argparse
 import json

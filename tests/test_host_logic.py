@@ -297,3 +297,13 @@ def test_pack_clip_batches_packs_in_order_across_video_boundaries():
     assert list(pack_clip_batches([videos[1]], [masks[1]], 4, pin=False)) == []
     with pytest.raises(ValueError):
         list(pack_clip_batches([videos[0], videos[0].float()], [masks[0], masks[0]], 4, pin=False))
+
+
+def test_host_pipelines_refuse_a_cpu_detector():
+    """The caller-loop drivers have no CPU path either: constructing them around a detector that is not on a CUDA
+    device raises instead of falling back."""
+    from dfdclip_b200.inference import HostClipPipeline, HostClipStream
+    det, _ = _detector()
+    for cls in (HostClipPipeline, HostClipStream):
+        with pytest.raises(RuntimeError):
+            cls(det)
