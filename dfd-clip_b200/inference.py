@@ -1,12 +1,17 @@
 """Video-level scoring driver: the caller loop of the reference's ``inference.py:107-156`` around the hot path.
 
-* ``predict_from_host``: clips in pinned host memory -> logits in host memory; the encoder runs chunk by chunk with
-  the H2D copies double-buffered on a copy stream, the decoder once per batch (the reference does a blocking
-  ``.to(device)`` / ``.to("cpu")`` around every chunk, inference.py:116-118).
-* ``shard_videos`` / ``score_videos``: videos are independent units, sharded across ranks by clip count; each rank
-  scores its videos (softmax per clip, mean over the clips of a video, inference.py:121,140) and ONE all_gather of
-  the per-video scores assembles the result on every rank (the reference gathers once per video, :147-149).
-  No collective runs inside the clip loop.
+* ``HostClipStream`` / ``predict_stream``: batch after batch of host clips in, host logits out, pipelined ACROSS
+  batches on three streams (H2D of batch k+1, encoder of batch k, decoder + D2H of batch k-1); the throughput path and
+  what ``bench.py`` reports as ``e2e``.
+* ``HostClipPipeline`` / ``predict_from_host``: one blocking call per batch (latency path): the encoder runs chunk by
+  chunk with the H2D copies double-buffered on a copy stream, the decoder once per batch (the reference does a
+  blocking ``.to(device)`` / ``.to("cpu")`` around every chunk, inference.py:116-118).
+* ``pack_clip_batches``: the ``torch.stack(clips[i:i + N])`` of inference.py:117 as a threaded packer into rotating
+  pinned staging buffers, across video boundaries.
+* ``shard_videos`` / ``score_videos`` / ``score_videos_batched``: videos are independent units, sharded across ranks
+  by clip count; each rank scores its videos (softmax per clip, mean over the clips of a video, inference.py:121,140;
+  ``video_mean_probs`` is a deterministic fp64 segment mean) and ONE all_gather of the per-video scores assembles the
+  result on every rank (the reference gathers once per video, :147-149). No collective runs inside the clip loop.
 """
 import torch
 
