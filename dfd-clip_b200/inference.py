@@ -141,19 +141,21 @@ class HostClipStream:
         self._taps = [None, None]  # per-slot tap buffers {layer: bf16 [rows, 3D]}
         self._out = [None, None]   # pinned host logits
 
-    def _slot_buffers(self, slot, x_host, m_host):
-        n, t = x_host.shape[:2]
+    def _slot_buffers(self, slot, n, x_tail, x_dtype, m_tail, m_dtype):
+        """Device input / mask buffers, tap buffers and pinned output of one slot for a batch of ``n`` clips of shape
+        ``x_tail`` (= [T, 3, R, R]) and masks of shape ``m_tail`` (= [T]); grown when a batch needs more."""
+        t = x_tail[0]
         # The copy stream is the first writer of the input buffers, so they come from ITS allocator pool: a block
         # handed out on the main stream may still be written by main-stream kernels that were launched (and whose
         # tensors were freed) earlier, which the copy stream does not wait for.
         with torch.cuda.stream(self.copy_stream):
             xb = self._x[slot]
-            if xb is None or xb.dtype != x_host.dtype or xb.shape[1:] != x_host.shape[1:] or xb.shape[0] < n:
+            if xb is None or xb.dtype != x_dtype or tuple(xb.shape[1:]) != tuple(x_tail) or xb.shape[0] < n:
                 self._x[slot] = None
-                xb = self._x[slot] = torch.empty(tuple(x_host.shape), dtype=x_host.dtype, device=self.dev)
+                xb = self._x[slot] = torch.empty((n,) + tuple(x_tail), dtype=x_dtype, device=self.dev)
             mb = self._m[slot]
-            if mb is None or mb.shape[1:] != m_host.shape[1:] or mb.shape[0] < n or mb.dtype != m_host.dtype:
-                mb = self._m[slot] = torch.empty(tuple(m_host.shape), dtype=m_host.dtype, device=self.dev)
+            if mb is None or tuple(mb.shape[1:]) != tuple(m_tail) or mb.shape[0] < n or mb.dtype != m_dtype:
+                mb = self._m[slot] = torch.empty((n,) + tuple(m_tail), dtype=m_dtype, device=self.dev)
         enc = self.det.encoder
         rows, cols = n * t * enc.tokens_per_frame, 3 * enc.width
         tap_slot = slot if self.dec_stream is not None else 0  # one stream -> the decoder is done before the next encoder
@@ -169,15 +171,24 @@ class HostClipStream:
         return xb, mb, taps, ob
 
     def _issue(self, slot, x_host, m_host):
-        """Enqueue copy, encoder and decoder of one batch; returns (event after the D2H copy, pinned logits view)."""
-        n, t = x_host.shape[:2]
+        """Enqueue copy, encoder and decoder of one batch; returns (event after the D2H copy, pinned logits view).
+        ``x_host`` / ``m_host`` are tensors, or equally long lists of tensors (pieces of pinned host memory that are
+        copied back to back into the device batch buffer: no host-side staging pass)."""
+        x_parts = list(x_host) if isinstance(x_host, (list, tuple)) else [x_host]
+        m_parts = list(m_host) if isinstance(m_host, (list, tuple)) else [m_host]
+        n, t = sum(int(p.shape[0]) for p in x_parts), x_parts[0].shape[1]
         det, main = self.det, torch.cuda.current_stream(self.dev)
-        xb, mb, taps, ob = self._slot_buffers(slot, x_host, m_host)
+        xb, mb, taps, ob = self._slot_buffers(slot, n, tuple(x_parts[0].shape[1:]), x_parts[0].dtype,
+                                              tuple(m_parts[0].shape[1:]), m_parts[0].dtype)
         copied, done = torch.cuda.Event(), torch.cuda.Event()
         # the slot's buffers are free: the batch that used them (two back) was synchronised before this call
         with torch.cuda.stream(self.copy_stream):
-            xb[:n].copy_(x_host, non_blocking=True)
-            mb[:n].copy_(m_host, non_blocking=True)
+            off = 0
+            for xp, mp in zip(x_parts, m_parts):
+                k = int(xp.shape[0])
+                xb[off:off + k].copy_(xp, non_blocking=True)
+                mb[off:off + k].copy_(mp, non_blocking=True)
+                off += k
             copied.record(self.copy_stream)
         main.wait_event(copied)
         det.encoder.encode(xb[:n].flatten(0, 1), keep_layers=det.layer_indices, qkv_into=taps)
@@ -199,7 +210,9 @@ class HostClipStream:
         pending = None
         out_dim = self.det.out_dim[0]
         for k, (x_host, m_host) in enumerate(batches):
-            if x_host.shape[0] == 0:
+            empty = (sum(int(p.shape[0]) for p in x_host) == 0) if isinstance(x_host, (list, tuple)) \
+                else x_host.shape[0] == 0
+            if empty:
                 cur = (None, torch.empty((0, out_dim), dtype=torch.float32))
             else:
                 cur = self._issue(k % 2, x_host, m_host)
@@ -286,7 +299,9 @@ def pack_clip_batches(videos, masks, batch_clips=64, pin=None, workers=4):
     64 fp32 clips is 308 MB of memcpy: longer than the GPU needs for the previous batch if done by one thread in the
     consumer's loop). A consumer may hold batch k until it asks for batch k+2, which is exactly what
     ``HostClipStream.run`` does (batch k-2 has been synchronised before batch k is requested). Nothing is
-    concatenated or pinned up front: host memory beyond the caller's videos is three batches."""
+    concatenated or pinned up front: host memory beyond the caller's videos is three batches. Videos that are ALREADY
+    pinned are not staged at all: their batches are yielded as lists of clip ranges (views), which
+    ``HostClipStream`` copies piece by piece into the device batch buffer."""
     from concurrent.futures import ThreadPoolExecutor
     step = max(1, int(batch_clips))
     first = next((v for v in videos if v.shape[0] > 0), None)
@@ -314,6 +329,13 @@ def pack_clip_batches(videos, masks, batch_clips=64, pin=None, workers=4):
                 cur, fill = [], 0
     if fill:
         plan.append((cur, fill))
+    if pin and all(v.is_pinned() and m.is_pinned() for v, m in zip(videos, masks) if v.shape[0] > 0):
+        # the caller's videos are already page-locked (e.g. a DataLoader with pin_memory=True): no staging pass at
+        # all — a batch is the list of clip ranges it consists of, and HostClipStream copies them back to back
+        # into its device batch buffer
+        for pieces, rows in plan:
+            yield ([videos[i][a:a + c] for i, a, c, _ in pieces], [masks[i][a:a + c] for i, a, c, _ in pieces])
+        return
     n_slots = min(3, len(plan))
     # staging buffers come from (and go back to) a small process-wide pool: page-locking 3 x 77 MB costs ~0.1 s, as
     # much as scoring 400 clips

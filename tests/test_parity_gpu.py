@@ -328,6 +328,10 @@ def test_video_level_scoring_with_the_real_detector(cuda_device):
     from dfdclip_b200.inference import score_videos_batched
     batched = score_videos_batched(det, videos, masks, batch_clips=7)  # batches cut across video boundaries
     assert torch.equal(torch.nan_to_num(batched), torch.nan_to_num(got))
+    # already-pinned videos take the no-staging path (clip ranges copied straight into the device batch buffer)
+    pinned = score_videos_batched(det, [v.pin_memory() for v in videos], [mm.pin_memory() for mm in masks],
+                                  batch_clips=7)
+    assert torch.equal(torch.nan_to_num(pinned), torch.nan_to_num(got))
     got = got.cpu()
     assert torch.isnan(got[3]).all()  # a video without clips is skipped (inference.py:109-111)
     keep = [i for i, c in enumerate(counts) if c > 0]
