@@ -3,6 +3,7 @@ U{8..32} one-second clips each (seed 3), video-level averaging — scored data-p
 over the ranks by clip count (shard_videos), every rank scores its shard through score_videos_batched (packer +
 HostClipStream, uint8 clips), ONE all_gather of per-video scores. Each rank materialises only the videos of its own
 shard (the others are zero-stride placeholders that only carry their shape). Rank 0 prints one JSON line.
+C3_PIN=1 page-locks each rank's videos first (a DataLoader with pin_memory=True): no staging pass in the driver.
 
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_c3_multi.py
 """
@@ -31,6 +32,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_videos, frames = int(os.environ.get("C3_VIDEOS", "560")), 8
+    pin_sources = os.environ.get("C3_PIN", "0") == "1"
     det, _ = build_detector("ViT-B/16", frames, dev)
     res = det.encoder.input_resolution
     g = torch.Generator().manual_seed(3)
@@ -42,10 +44,12 @@ def main():
     for i, n in enumerate(counts):
         if i in mine:
             idx = torch.randint(0, 64, (n,), generator=gr)
-            videos.append(pool[idx].clone())
+            v = pool[idx].clone()
+            videos.append(v.pin_memory() if pin_sources else v)  # C3_PIN=1: what a pinning DataLoader delivers
         else:
             videos.append(torch.zeros((), dtype=torch.uint8).expand(n, frames, 3, res, res))
-        masks.append(torch.ones((n, frames), dtype=torch.bool))
+        mk = torch.ones((n, frames), dtype=torch.bool)
+        masks.append(mk.pin_memory() if (pin_sources and i in mine) else mk)
     with torch.no_grad():
         warm = sorted(mine)[:4]  # warm-up without collectives: this rank's first videos through the same pipeline
         list(HostClipStream(det).run(pack_clip_batches([videos[i] for i in warm], [masks[i] for i in warm], 64)))
@@ -70,7 +74,7 @@ def main():
     if rank == 0:
         line = {"config": "C3: %d synthetic videos, %d clips (U{8..32} per video, seed 3), ViT-B/16, 8 frames, uint8 clips, "
                           "video-level mean of clip probabilities" % (n_videos, sum(counts)),
-                "n_gpus": world, "seconds": dt, "clips_per_s": sum(counts) / dt, "videos_per_s": n_videos / dt,
+                "n_gpus": world, "page_locked_videos": pin_sources, "seconds": dt, "clips_per_s": sum(counts) / dt, "videos_per_s": n_videos / dt,
                 "clips_on_rank0": sum(counts[i] for i in mine), "scores_finite": bool(torch.isfinite(scores).all().item()),
                 "scores_identical_on_all_ranks": same,
                 "api": "dfdclip_b200.inference.score_videos_batched (shard_videos + pack_clip_batches + HostClipStream, "
