@@ -211,6 +211,36 @@ def timing_read(device):
     return {lib.dfd_timing_tag_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
 
 
+class Workspace:
+    """A grow-only scratch buffer of a module. A CUDA graph that captured a launch has the buffer's address baked in,
+    so once a buffer has been handed out under stream capture it is never freed: a later, larger request allocates a
+    new buffer and the old one is kept alive for the graphs that reference it (replaying after an eager call with a
+    bigger batch would otherwise read and write memory already returned to the caching allocator)."""
+
+    def __init__(self):
+        self.buf = None
+        self.captured = False
+        self.retired = []
+
+    def numel(self):
+        return 0 if self.buf is None else self.buf.numel()
+
+    def get(self, nbytes, device):
+        nbytes = max(int(nbytes), 16)
+        buf = self.buf
+        capturing = torch.cuda.is_current_stream_capturing()
+        if buf is None or buf.numel() < nbytes or buf.device != device:
+            if buf is not None and self.captured:
+                self.retired.append(buf)
+            self.buf = None  # release before growing (unless a graph may still reference it)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.buf = buf
+            self.captured = False
+        if capturing:
+            self.captured = True
+        return buf
+
+
 def stream_ptr(device=None):
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -418,18 +448,19 @@ def adapter_apply(kind, kv, rows, ld, width, inner, w_down, w_mid, w_up, ln_weig
                   workspace=None):
     """In-place CompInvAdapter on one bf16 tap: ``kv`` is a tensor whose data pointer is the first element of a
     ``[rows, width]`` matrix with row pitch ``ld`` elements (a K or V column slice of a packed QKV buffer).
-    Weights: bf16 matrices, fp32 LayerNorm parameters. Returns the workspace tensor (reusable)."""
+    Weights: bf16 matrices, fp32 LayerNorm parameters. Returns the ``Workspace`` (reusable)."""
     lib = load_library()
     dev = kv.device
     assert kv.dtype == torch.bfloat16
     if rows == 0:
         return workspace
     nbytes = lib.dfd_adapter_workspace_bytes(kind, width, inner, rows)
-    if workspace is None or workspace.numel() < nbytes or workspace.device != dev:
-        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    if workspace is None:
+        workspace = Workspace()
+    buf = workspace.get(nbytes, dev)
     w = AdapterWeights(ptr(w_down).value, ptr(w_mid).value, ptr(w_up).value, ptr(ln_weight).value, ptr(ln_bias).value)
     check(lib.dfd_adapter_apply(ctx(dev), kind, width, inner, ctypes.byref(w), ptr(kv), ld, rows, group_rows,
-                                group_skip, ptr(workspace), workspace.numel(), stream_ptr(dev)))
+                                group_skip, ptr(buf), buf.numel(), stream_ptr(dev)))
     return workspace
 
 

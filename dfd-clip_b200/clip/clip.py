@@ -17,12 +17,12 @@ _MODELS = {
     "ViT-B/32": "https://openaipublic.azureedge.net/clip/models/40d365715913c9da98579312b702a82c18be219cc2a73407c4526f58eba950af/ViT-B-32.pt",
     "ViT-B/16": "https://openaipublic.azureedge.net/clip/models/5806e77cd80f8b59890b7e101eabd078d9fb84e6937f9e85e4ecb61988df416f/ViT-B-16.pt",
     "ViT-L/14": "https://openaipublic.azureedge.net/clip/models/b8cca3fd41ae0c99ba7e8951adf17d267cdb84cd88be6f7c2e0eca1737a03836/ViT-L-14.pt",
-    "ViT-L/14@336px": "https://openaipublic.azureedge.net/clip/models/3035c92b350959924f9f00213499208652fc7ea050643e8b385c2dac08641f02/ViT-L-14-336px.pt",
 }
 
 
 def available_models() -> List[str]:
-    """Names of the CLIP ViT models this loader knows (the ResNet towers are not supported by the B200 path)."""
+    """Names of the CLIP ViT models this loader knows. The ResNet towers and ``ViT-L/14@336px`` (577 tokens per
+    frame; the attention kernels hold a frame's keys on chip, at most 272) are not supported by the B200 path."""
     return list(_MODELS.keys())
 
 

@@ -16,6 +16,9 @@ from torch import nn
 from .. import _native
 
 
+MAX_TOKENS_PER_FRAME = 272   # csrc/encoder.cu vit_shape: a frame's keys stay on chip in the attention kernels
+
+
 class LayerNorm(nn.LayerNorm):
     """Parameter holder for a LayerNorm (eps 1e-5); also usable as a module (fp32 math like :157-163)."""
 
@@ -65,8 +68,9 @@ class Transformer(nn.Module):
 class VisionTransformer(nn.Module):
     """CLIP ViT frame encoder. ``forward(x[N,3,R,R], with_out=False, with_q=False)`` returns, like the reference
     (:276-294, :236-251), one dict per layer with ``k``, ``v`` (and ``q`` / ``out`` on request), each k/v/q a
-    strided ``[N, L, H, 64]`` view of that layer's packed ``[N*L, 3D]`` QKV buffer. Tensors are bf16 (the compute
-    dtype of the B200 path) except ``out`` (fp32 residual stream)."""
+    ``[N, L, H, 64]`` tensor in fp32 like the reference's (:186-199; ``tap_dtype``), converted from that layer's packed
+    bf16 ``[N*L, 3D]`` QKV buffer — the B200 path's compute dtype, which ``encode`` hands out without a copy and which
+    ``Detector`` reads in place. ``out`` is the fp32 residual stream."""
 
     def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
         super().__init__()
@@ -87,7 +91,10 @@ class VisionTransformer(nn.Module):
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
         self._packed = None
         self._packed_key = None
-        self._workspace = None
+        self._workspace = _native.Workspace()
+        # dtype of the q/k/v tensors ``forward`` returns: fp32 as in the reference; torch.bfloat16 hands out views of
+        # the packed buffers instead (no conversion pass)
+        self.tap_dtype = torch.float32
         # normalisation applied on the fly to uint8 frames: the constants of the reference's CLIP transform
         # (src/models.py:762-768); Detector overrides them when its transform uses other values
         self.input_mean = (0.48145466, 0.4578275, 0.40821073)
@@ -168,12 +175,7 @@ class VisionTransformer(nn.Module):
         return packed
 
     def _get_workspace(self, nbytes, dev):
-        ws = self._workspace
-        if ws is None or ws.numel() < nbytes or ws.device != dev:
-            self._workspace = None  # release before growing
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self._workspace = ws
-        return ws
+        return self._workspace.get(nbytes, dev)
 
     def encode(self, x, keep_layers=None, need_out=False, last_qkv_only=None, qkv_into=None, frame_offset=0):
         """``qkv_into`` (optional): dict layer -> preallocated bf16 ``[N_total*L, 3D]`` buffer; the rows of these
@@ -263,9 +265,9 @@ class VisionTransformer(nn.Module):
         kvs = []
         for l in range(self.layers):
             view = qkv[l].view(n, seq, 3, h, 64)
-            a = dict(k=view[:, :, 1], v=view[:, :, 2])
+            a = dict(k=view[:, :, 1].to(self.tap_dtype), v=view[:, :, 2].to(self.tap_dtype))
             if with_q:
-                a["q"] = view[:, :, 0]
+                a["q"] = view[:, :, 0].to(self.tap_dtype)
             if with_out:
                 a["out"] = outs[l]
             kvs.append(a)
@@ -318,6 +320,10 @@ def build_model(state_dict):
     grid_size = round((state_dict["visual.positional_embedding"].shape[0] - 1) ** 0.5)
     image_resolution = vision_patch_size * grid_size
     embed_dim = state_dict["visual.proj"].shape[1]
+    if grid_size * grid_size + 1 > MAX_TOKENS_PER_FRAME:  # fail at load time, not at the first encode
+        raise NotImplementedError("%d tokens per frame (resolution %d, patch %d): the B200 attention kernels support at "
+                                  "most %d" % (grid_size * grid_size + 1, image_resolution, vision_patch_size,
+                                               MAX_TOKENS_PER_FRAME))
     model = CLIP(embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size)
     visual = OrderedDict((k[len("visual."):], v.float()) for k, v in state_dict.items() if k.startswith("visual."))
     model.visual.load_state_dict(visual)

@@ -451,7 +451,15 @@ def score_videos(predict_fn, videos, masks, chunk_clips=16, group=None, device=N
         out_dim = logits.shape[1]
         local.append(video_mean_probs(logits, [counts[i]])[0])
     ref = next((t for t in local if t is not None), None)
-    tdev = ref.device if ref is not None else (torch.device(device) if device is not None else torch.device("cpu"))
+    if ref is not None:
+        tdev = ref.device
+    elif device is not None:
+        tdev = torch.device(device)
+    elif distributed and dist.get_backend(group) == "nccl":
+        # a rank whose shard holds no clips must still join the collectives with CUDA tensors like its peers
+        tdev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        tdev = torch.device("cpu")
     if distributed:
         od = torch.tensor([out_dim or 0], device=tdev)
         dist.all_reduce(od, op=dist.ReduceOp.MAX, group=group)

@@ -202,7 +202,7 @@ class Decoder(nn.Module):
             self.task_projections.append(mats)
         self._wcache = None
         self._gp_cache = {}
-        self._workspace = None
+        self._workspace = _native.Workspace()
 
     # ------------------------------------------------------------------------------------------ native
     def _native_weights(self):
@@ -351,10 +351,8 @@ class Decoder(nn.Module):
         block_out = torch.empty((b, nb, d), dtype=torch.float32, device=dev)
         video_feature = torch.empty((b, d), dtype=torch.float32, device=dev)
         ws_bytes = lib.dfd_decoder_workspace_bytes(b, t, p, d, nb, self.attn_mode)
-        if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
-            self._workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         return dict(dev=dev, b=b, t=t, p=p, nb=nb, w=w, taps=taps, mask=mask, block_out=block_out,
-                    video_feature=video_feature, ws=self._workspace, ws_bytes=ws_bytes, copied=copied,
+                    video_feature=video_feature, ws=self._workspace.get(ws_bytes, dev), ws_bytes=ws_bytes, copied=copied,
                     keep_alive=(keep, karr, varr))
 
     def _finish(self, plan, logit_scale):
@@ -456,7 +454,7 @@ class CompInvAdapter(nn.Module):
                 blk[j] = mod
             self.layer_blocks.append(blk)
         self._bf16 = {}
-        self._workspace = None
+        self._workspace = _native.Workspace()
 
     # ------------------------------------------------------------------------------------------ native
     def needs_autograd(self):

@@ -235,3 +235,34 @@ def make_clips(batch, num_frames, image_size, seed=7, masked_tail=True):
             m[1, -2:] = False
         m[4::5, -1] = False
     return x, m
+
+
+def make_varied_clips(batch, num_frames, image_size, seed=7, video_ids=None, masked_tail=True):
+    """Clips with content, unlike ``make_clips``' iid noise: every video has its own coarse colour layout, every clip
+    its own mid-scale texture, contrast and brightness, every frame its own pixel noise — so the video features (and
+    the class margins of a random head) differ from clip to clip the way they do on real videos. Built from exact
+    operations only (block replication, elementwise fp32 multiply / add), so the same bits come out on every host.
+    ``video_ids`` [batch] groups clips into videos (default: one video per clip). Returns x fp32 [B,T,3,R,R] and
+    m bool [B,T] with the same trailing-frame padding pattern as ``make_clips``."""
+    r = image_size
+    coarse_n, mid_n = max(1, r // 32), max(1, r // 8)
+    video_ids = list(range(batch)) if video_ids is None else [int(v) for v in video_ids]
+    x = torch.empty(batch, num_frames, 3, r, r, dtype=torch.float32)
+    for b in range(batch):
+        gv = _gen(seed, "video%d" % video_ids[b])
+        coarse = torch.randn(3, coarse_n, coarse_n, generator=gv)
+        gc = _gen(seed, "clip%d" % b)
+        mid = torch.randn(3, mid_n, mid_n, generator=gc)
+        contrast = 0.5 + torch.rand((), generator=gc)
+        brightness = 0.5 * torch.randn((), generator=gc)
+        noise_std = 0.25 + 0.5 * torch.rand((), generator=gc)
+        base = coarse.repeat_interleave(r // coarse_n, 1).repeat_interleave(r // coarse_n, 2) \
+            + 0.5 * mid.repeat_interleave(r // mid_n, 1).repeat_interleave(r // mid_n, 2)
+        noise = torch.randn(num_frames, 3, r, r, generator=gc)
+        x[b] = (base[None] + noise * noise_std) * contrast + brightness
+    m = torch.ones(batch, num_frames, dtype=torch.bool)
+    if masked_tail and num_frames > 2:
+        if batch > 1:
+            m[1, -2:] = False
+        m[4::5, -1] = False
+    return x, m

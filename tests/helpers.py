@@ -53,6 +53,26 @@ def golden_inputs(g):
     return sd, x, m
 
 
+# full-size cases of oracle/gen_golden_full.py: name -> seed of synthetic.make_varied_clips
+FULLSIZE_SEEDS = {"vitb16_c2": 7, "vitl14_c4": 7, "vitb16_c5": 17, "vitb16_c3": 27}
+
+
+def fullsize_inputs(name, g, clips=None):
+    """(state_dict, clips, mask) of a BASELINE-size golden case: varied synthetic clips and the task head stored in
+    the fixture (gen_golden_full.py centres it on the reference's own features). ``clips`` = slice of the batch."""
+    from dfdclip_b200 import synthetic
+    dims = synthetic.vit_dims(g["arch"])
+    sd = synthetic.detector_state_dict(g["arch"], g["num_frames"], out_dims=(2,), taps=g["layer_indices"], seed=0)
+    sd["decoder.proj0x2"] = torch.from_numpy(g["proj0x2"]).clone()
+    video_ids = [int(v) for v in g["video_ids"]] if "video_ids" in g else None
+    x, m = synthetic.make_varied_clips(g["batch"], g["num_frames"], dims["image_size"], seed=FULLSIZE_SEEDS[name],
+                                       video_ids=video_ids)
+    assert np.array_equal(m.numpy(), g["mask"])
+    if clips is not None:
+        x, m = x[clips], m[clips]
+    return sd, x, m
+
+
 def golden_tensor(g, key, layer, like):
     """Golden values for tap `key` of `layer`: (reference values, matching values taken from `like`)."""
     like = like.contiguous().float().cpu()

@@ -307,3 +307,43 @@ def test_host_pipelines_refuse_a_cpu_detector():
     for cls in (HostClipPipeline, HostClipStream):
         with pytest.raises(RuntimeError):
             cls(det)
+
+
+def test_reference_arm_of_bench_runs_the_staged_reference(tmp_path):
+    """`bench.py --impl reference` prints the contract's JSON line; with the reference staged under baseline/_ref (or at
+    /root/reference) the arm is the unmodified reference (`kind: reference`), otherwise the oracle port."""
+    import json
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_runner
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--arch", "tiny-256x4",
+                          "--frames", "4", "--steps", "2", "--warmup", "1", "--ref-clips", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "clips/s"
+    assert line["cpu_baseline"]["kind"] == ("reference" if reference_runner.reference_root() else "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+def test_staged_reference_reproduces_the_golden_vectors():
+    """baseline/_ref (oracle/stage_reference.py) holds the reference files byte for byte: run from there, the
+    reference's Detector gives the committed golden logits bit for bit."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_runner
+    import stage_reference
+    root = stage_reference.staged_root()
+    if root is None:
+        pytest.skip("reference not staged (baseline/_ref is written by __graft_entry__.build() in the build container)")
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]   # an earlier import from another root
+    det = reference_runner.build_reference_detector("tiny-256x4", 4, root=root)
+    from dfdclip_b200 import synthetic
+    x, m = synthetic.make_clips(3, 4, 32, seed=7)
+    with torch.no_grad():
+        logits = det.predict(x, m)[0][0].numpy()
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "reference_tiny.npz"))["logits"]
+    assert np.array_equal(logits, golden)
