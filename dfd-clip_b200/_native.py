@@ -29,6 +29,9 @@ EXPORTS = (
     "dfd_decoder_attention_modes_workspace_bytes", "dfd_decoder_attention_modes",
     "dfd_patchify_u8", "dfd_encoder_forward_u8", "dfd_gemm_bf16_ln", "dfd_predict_forward",
     "dfd_linear_f32_workspace_bytes", "dfd_linear_f32",
+    "dfd_resize_crop_u8_workspace_bytes", "dfd_resize_crop_u8",
+    "dfd_decoder_train_bytes", "dfd_decoder_train_forward", "dfd_decoder_train_backward",
+    "dfd_linear_f32_backward_workspace_bytes", "dfd_linear_f32_backward",
 )
 
 
@@ -149,6 +152,23 @@ def load_library():
                                                        c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                        c_size_t, c_void_p]
+        lib.dfd_resize_crop_u8_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        lib.dfd_resize_crop_u8_workspace_bytes.restype = c_size_t
+        lib.dfd_resize_crop_u8.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                           c_void_p]
+        lib.dfd_decoder_train_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        lib.dfd_decoder_train_bytes.restype = c_size_t
+        lib.dfd_decoder_train_forward.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
+                                                  ctypes.POINTER(KvTaps), c_void_p, c_int, c_int, c_int, c_void_p,
+                                                  c_void_p, c_size_t, c_void_p]
+        lib.dfd_decoder_train_backward.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
+                                                   ctypes.POINTER(DecoderWeights), ctypes.POINTER(KvTaps), c_void_p,
+                                                   c_int, c_int, c_int, c_void_p, _PP, _PP, c_void_p, c_size_t,
+                                                   c_void_p]
+        lib.dfd_linear_f32_backward_workspace_bytes.argtypes = [c_int, c_int, c_int]
+        lib.dfd_linear_f32_backward_workspace_bytes.restype = c_size_t
+        lib.dfd_linear_f32_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         lib.dfd_adapter_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int64]
         lib.dfd_adapter_workspace_bytes.restype = c_size_t
         lib.dfd_adapter_apply.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(AdapterWeights), c_void_p,
@@ -444,6 +464,22 @@ def decoder_attention_backward(qs, k, v, pos_emb, mask, stats, dmix, need_kv_gra
     return dqs, dpe
 
 
+def linear_f32_backward(x, weight, dy, gelu_pre=None, dx_add=None, need_dx=True, need_dw=True):
+    """Backward of ``linear_f32`` (x [B,K], weight [N,K], dy [B,N]): returns (dx [B,K], dW [N,K], db [N])."""
+    b, k = x.shape
+    n = weight.shape[0]
+    dev = x.device
+    dx = torch.empty((b, k), dtype=torch.float32, device=dev) if need_dx else None
+    dw = torch.empty((n, k), dtype=torch.float32, device=dev) if need_dw else None
+    db = torch.empty((n,), dtype=torch.float32, device=dev) if need_dw else None
+    lib = load_library()
+    nbytes = lib.dfd_linear_f32_backward_workspace_bytes(b, n, k)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    check(lib.dfd_linear_f32_backward(ctx(dev), ptr(x), ptr(weight), ptr(dy), ptr(gelu_pre), ptr(dx_add), ptr(dx),
+                                      ptr(dw), ptr(db), b, n, k, ptr(ws), nbytes, stream_ptr(dev)))
+    return dx, dw, db
+
+
 def adapter_apply(kind, kv, rows, ld, width, inner, w_down, w_mid, w_up, ln_weight, ln_bias, group_rows, group_skip,
                   workspace=None):
     """In-place CompInvAdapter on one bf16 tap: ``kv`` is a tensor whose data pointer is the first element of a
@@ -462,6 +498,32 @@ def adapter_apply(kind, kv, rows, ld, width, inner, w_down, w_mid, w_up, ln_weig
     check(lib.dfd_adapter_apply(ctx(dev), kind, width, inner, ctypes.byref(w), ptr(kv), ld, rows, group_rows,
                                 group_skip, ptr(buf), buf.numel(), stream_ptr(dev)))
     return workspace
+
+
+def resize_crop_u8(frames, size, workspace=None):
+    """``T.Resize(size, BICUBIC)`` + ``T.CenterCrop(size)`` of the loader transform (reference src/models.py:756-761)
+    on the device: uint8 frames ``[..., 3, H, W]`` -> uint8 ``[..., 3, size, size]`` (within 1 LSB of torchvision)."""
+    if frames.dtype != torch.uint8 or frames.dim() < 3 or frames.shape[-3] != 3:
+        raise ValueError("resize_crop_u8 expects uint8 frames [..., 3, H, W], got %s %s" % (frames.dtype, tuple(frames.shape)))
+    if frames.device.type != "cuda":
+        raise NativeError("dfdclip_b200 resize needs CUDA tensors (no CPU fallback)")
+    lead = tuple(frames.shape[:-3])
+    h, w = int(frames.shape[-2]), int(frames.shape[-1])
+    flat = frames.reshape(-1, 3, h, w).contiguous()
+    n = flat.shape[0]
+    out = torch.empty((n, 3, size, size), dtype=torch.uint8, device=frames.device)
+    if n == 0:
+        return out.view(lead + (3, size, size))
+    lib = load_library()
+    nbytes = lib.dfd_resize_crop_u8_workspace_bytes(n, h, w, size)
+    if nbytes == 0:
+        raise NativeError("unsupported resize %dx%d -> %d" % (h, w, size))
+    if workspace is None:
+        workspace = Workspace()
+    buf = workspace.get(nbytes, frames.device)
+    check(lib.dfd_resize_crop_u8(ctx(frames.device), ptr(flat), n, h, w, size, ptr(out), ptr(buf), buf.numel(),
+                                 stream_ptr(frames.device)))
+    return out.view(lead + (3, size, size))
 
 
 def ema_frames(x, ratio):

@@ -92,6 +92,7 @@ class VisionTransformer(nn.Module):
         self._packed = None
         self._packed_key = None
         self._workspace = _native.Workspace()
+        self._resize_workspace = _native.Workspace()
         # dtype of the q/k/v tensors ``forward`` returns: fp32 as in the reference; torch.bfloat16 hands out views of
         # the packed buffers instead (no conversion pass)
         self.tap_dtype = torch.float32
@@ -207,6 +208,11 @@ class VisionTransformer(nn.Module):
     def _encode_plan(self, x, keep_layers=None, need_out=False, last_qkv_only=None, qkv_into=None, frame_offset=0):
         """Argument checking, output / workspace buffers and pointer arrays of one encoder pass (everything ``encode``
         does short of the launch; ``Detector.predict`` hands the same plan to ``dfd_predict_forward``)."""
+        if x.dim() == 4 and x.dtype == torch.uint8 and x.shape[1] == 3 and x.device.type == "cuda" and \
+                (x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution):
+            # raw decoded frames of another size: the loader's Resize(BICUBIC) + CenterCrop on the device
+            # (reference src/models.py:756-761), then the uint8 path below
+            x = _native.resize_crop_u8(x, self.input_resolution, self._resize_workspace)
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
             raise ValueError("expected frames of shape [N,3,%d,%d], got %s" %
                              (self.input_resolution, self.input_resolution, tuple(x.shape)))

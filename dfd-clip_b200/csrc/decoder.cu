@@ -199,12 +199,13 @@ linear_partial_kernel(const float* __restrict__ x, const float* __restrict__ W, 
 
 template <bool QGELU>
 __global__ void linear_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
-                                     const float* res, float* out, int B, int N) {
+                                     const float* res, float* out, int B, int N, float* pre_out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(B) * N;
   if (i >= total) return;
   float v = bias ? bias[i % N] : 0.f;
   for (int s = 0; s < splits; ++s) v += part[s * total + i];
+  if (pre_out) pre_out[i] = v;  // the pre-activation, saved for the training step's backward
   if (QGELU) v = v / (1.f + __expf(-1.702f * v));
   if (res) v += res[i];
   out[i] = v;
@@ -217,7 +218,7 @@ size_t linear_workspace_bytes(int B, int max_n) {
 }
 
 int linear_f32(const dfd_ctx* ctx, const float* x, const float* W, const float* bias, const float* res, float* out,
-               int B, int N, int K, bool qgelu, float* part, cudaStream_t stream) {
+               int B, int N, int K, bool qgelu, float* part, cudaStream_t stream, float* pre_out = nullptr) {
   DFD_CHECK_ARG(K % 4 == 0, "linear_f32: K=%d must be a multiple of 4", K);
   const int n_tiles = (N + LIN_BN - 1) / LIN_BN, b_tiles = (B + LIN_BM - 1) / LIN_BM;
   // enough k-splits to cover the SMs about twice, each at least one BK step, at most LIN_MAX_SPLITS
@@ -235,9 +236,9 @@ int linear_f32(const dfd_ctx* ctx, const float* x, const float* W, const float* 
   const int64_t total = static_cast<int64_t>(B) * N;
   const unsigned rgrid = static_cast<unsigned>((total + 255) / 256);
   if (qgelu)
-    linear_reduce_kernel<true><<<rgrid, 256, 0, stream>>>(part, splits, bias, res, out, B, N);
+    linear_reduce_kernel<true><<<rgrid, 256, 0, stream>>>(part, splits, bias, res, out, B, N, pre_out);
   else
-    linear_reduce_kernel<false><<<rgrid, 256, 0, stream>>>(part, splits, bias, res, out, B, N);
+    linear_reduce_kernel<false><<<rgrid, 256, 0, stream>>>(part, splits, bias, res, out, B, N, pre_out);
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
 }

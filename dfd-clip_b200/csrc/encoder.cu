@@ -37,13 +37,16 @@ int fold_ln_linear(const float* W, const float* bias, const float* gamma, const 
 // on the power-capped B200 the removed LayerNorm passes (-1.65 ms per C2 step) are almost entirely paid back by the
 // heavier GEMM epilogues (+1.0 .. +1.4 ms), the step moves by 0 .. 1.7 %, so the separate
 // LayerNorm kernels stay the default.
-static bool ln_fuse_enabled() {
-  static const bool v = []() {
+// DFD_LN_FUSE: 0 = separate LayerNorm kernels, 1 = ln_1 and ln_2 folded, 2 = only ln_1 folded (its producer is the
+// c_proj GEMM, K = 4D, whose epilogue has slack; ln_2 behind the short out-proj GEMM stays a kernel).
+static int ln_fuse_mode() {
+  static const int v = []() {
     const char* e = getenv("DFD_LN_FUSE");
-    return e ? atoi(e) != 0 : false;
+    return e ? atoi(e) : 0;
   }();
   return v;
 }
+static bool ln_fuse_enabled() { return ln_fuse_mode() != 0; }
 
 static inline size_t up256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
@@ -254,6 +257,7 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
   resid.bf16_out = u;
   resid.ld_bf16 = D;
 
+  const bool fuse_fc = fuse && ln_fuse_mode() == 1;  // ln_2 folded into c_fc as well (out-proj emits bf16(x) + stats)
   for (int l = 0; l < num_run_layers && fuse; ++l) {
     const size_t lb = pl.layer0 + pl.layer_stride * l;
     void* qkv = (qkv_out && qkv_out[l]) ? qkv_out[l] : static_cast<void*>(ws + wl.qkv);
@@ -272,11 +276,21 @@ int encoder_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
                                              3 * D, D, DFD_EPI_STORE_BF16_LNFOLD, &fold_in, stream));
     if (after_qkv) DFD_TRY(after_qkv(l));
     DFD_TIMED(DFD_TAG_MHA, mha_fwd(ctx, qkv, mix, n_frames, s.L, s.H, stream));
-    DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16_ln(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
-                                             DFD_EPI_RESID_LN_F32, &resid, stream));
-    fold_in.colsum = f32p(lb + pl.c_fc);
-    DFD_TIMED(DFD_TAG_GEMM_FC, gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_fc, D, f32p(lb + pl.bf_fc), hid, 4 * D, M,
-                                            4 * D, D, DFD_EPI_STORE_BF16_QGELU_LNFOLD, &fold_in, stream));
+    if (fuse_fc) {
+      DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16_ln(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
+                                               DFD_EPI_RESID_LN_F32, &resid, stream));
+      fold_in.colsum = f32p(lb + pl.c_fc);
+      DFD_TIMED(DFD_TAG_GEMM_FC, gemm_bf16_ln(ctx, u, D, pk + lb + pl.wf_fc, D, f32p(lb + pl.bf_fc), hid, 4 * D, M,
+                                              4 * D, D, DFD_EPI_STORE_BF16_QGELU_LNFOLD, &fold_in, stream));
+    } else {
+      DFD_TIMED(DFD_TAG_GEMM_OUT, gemm_bf16(ctx, mix, D, pk + lb + pl.w_out, D, f32p(lb + pl.b_out), x, D, M, D, D,
+                                            DFD_EPI_ADD_F32, stream));
+      DFD_TIMED(DFD_TAG_LAYERNORM,
+                layernorm(x, f32p(lb + pl.ln2_w), f32p(lb + pl.ln2_b), nullptr, 0, u, nullptr, M, D, stream));
+      DFD_TIMED(DFD_TAG_GEMM_FC, gemm_bf16(ctx, u, D, pk + lb + pl.w_fc, D, f32p(lb + pl.b_fc), hid, 4 * D, M, 4 * D,
+                                           D, DFD_EPI_STORE_BF16_QGELU, stream));
+    }
+    // the c_proj epilogue refreshes bf16(x) (in `u`) and the row statistics for the next layer's folded ln_1
     DFD_TIMED(DFD_TAG_GEMM_PROJ, gemm_bf16_ln(ctx, hid, 4 * D, pk + lb + pl.w_proj, 4 * D, f32p(lb + pl.b_proj), x, D,
                                               M, D, 4 * D, DFD_EPI_RESID_LN_F32, &resid, stream));
     if (x_out && x_out[l])

@@ -153,6 +153,83 @@ class _DecoderAttentionFn(torch.autograd.Function):
         return dqs, dpe, dk, dv, None
 
 
+def _mode_attention_autograd(qs, pos_emb, k, v, m, attn_mode):
+    """Decoder attention for ``op_mode.attn_mode`` ("frame" / "temporal" softmax groups, reference :107-115) under
+    autograd, for the TRAINING step of those configurations: plain torch fp32 ops on the tapped K/V (inference uses the
+    native ``dfd_decoder_attention_modes`` kernels). qs [B,H,128], k / v [B,T,P,H,64], m bool [B,T] -> mix [B, H*64]."""
+    b, t, p, h, dh = k.shape
+    kf, vf = k.float(), v.float()
+    if pos_emb is not None:
+        pe = pos_emb.view(1, t, 1, h, dh)
+        kf, vf = kf + pe, vf + pe
+    q0, q1 = qs[..., :dh], qs[..., dh:]
+    mm = m.view(b, t, 1, 1)
+    s = torch.einsum("bhc,btphc->btph", q0 / dh ** 0.5, kf).masked_fill(~mm, float("-inf"))
+    a0 = 0
+    if attn_mode & _native.ATTN_FRAME:
+        a0 = a0 + s.softmax(dim=2)       # over the patches of each frame
+    if attn_mode & _native.ATTN_TEMPORAL:
+        a0 = a0 + s.softmax(dim=1)       # over the frames of each patch position
+    a1 = torch.einsum("bhc,btphc->btph", q1 / dh ** 0.5, kf).tanh()
+    gate = -(q1.view(b, 1, 1, h, dh) - kf).abs().sum(-1) / dh ** 0.5
+    gate = 2 * gate.sigmoid().masked_fill(~mm, 0.0)
+    aff = (a0 + a1 * gate) / 2
+    return torch.einsum("btph,btphc->bhc", aff, vf).flatten(-2)
+
+
+class _DecoderChainFn(torch.autograd.Function):
+    """The decoder's whole one-token chain (reference :336-338, 259-269, 173-176, 136-146) as ONE autograd node with a
+    native forward (``dfd_decoder_train_forward``: activations saved in a library-defined buffer) and a hand-written
+    native backward (``dfd_decoder_train_backward``: weight gradients as rank-B outer products, LayerNorm / QuickGELU /
+    attention backward kernels), instead of ~700 torch kernels per step. Inputs after the three non-tensor arguments
+    are the chain's parameters in ``Decoder._chain_params`` order; the output is the stack of block outputs
+    ``[B, n_blocks, D]`` (ln_post, projections and the loss stay torch ops on ``[B, D]`` tensors).
+
+    Gradients go to fresh tensors (autograd accumulates them into ``.grad`` as usual, so DDP hooks see them), or — when
+    the decoder holds a ``_grad_sink`` (``training.TrainStep``) — straight into the caller's flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, decoder, kvs, m, *params):
+        plan = decoder._run_plan(kvs, m)
+        lib, dev = _native.load_library(), plan["dev"]
+        d, h, nb, b, t, p = decoder.width, decoder.heads, plan["nb"], plan["b"], plan["t"], plan["p"]
+        nbytes = lib.dfd_decoder_train_bytes(b, t, d, nb)
+        saved = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.dfd_decoder_train_forward(
+                _native.ctx(dev), d, h, nb, ctypes.byref(plan["w"]), ctypes.byref(plan["taps"]),
+                _native.ptr(plan["mask"]), b, t, p, _native.ptr(plan["block_out"]), _native.ptr(saved), nbytes,
+                _native.stream_ptr(dev)))
+        ctx.decoder, ctx.plan, ctx.saved_buf, ctx.nbytes = decoder, plan, saved, nbytes
+        ctx.params = params
+        return plan["block_out"]
+
+    @staticmethod
+    def backward(ctx, d_block_out):
+        decoder, plan = ctx.decoder, ctx.plan
+        lib, dev = _native.load_library(), plan["dev"]
+        d, h, nb, b, t, p = decoder.width, decoder.heads, plan["nb"], plan["b"], plan["t"], plan["p"]
+        d_block_out = d_block_out.contiguous().float()
+        sink = getattr(decoder, "_grad_sink", None) or {}
+        grads, returned = [], []
+        for prm in ctx.params:
+            buf = sink.get(id(prm))
+            if buf is None:
+                buf = torch.empty_like(prm, memory_format=torch.contiguous_format)
+                returned.append(buf)
+            else:
+                returned.append(None)  # written in place into the caller's gradient buffer
+            grads.append(buf)
+        gw, keep = decoder._weights_struct(grads)
+        with torch.cuda.device(dev):
+            _native.check(lib.dfd_decoder_train_backward(
+                _native.ctx(dev), d, h, nb, ctypes.byref(plan["w"]), ctypes.byref(gw), ctypes.byref(plan["taps"]),
+                _native.ptr(plan["mask"]), b, t, p, _native.ptr(d_block_out), None, None, _native.ptr(ctx.saved_buf),
+                ctx.nbytes, _native.stream_ptr(dev)))
+        del keep
+        return (None, None, None) + tuple(returned)
+
+
 class Decoder(nn.Module):
     """Temporal decoder: a learnable CLS query cross-attends (softmax + CoDA) to the tapped K/V of all T*P patch
     tokens of a clip, block by block, then ``ln_post`` and the task projection(s) (reference :272-361)."""
@@ -205,43 +282,61 @@ class Decoder(nn.Module):
         self._workspace = _native.Workspace()
 
     # ------------------------------------------------------------------------------------------ native
+    def _chain_params(self):
+        """Parameters of the one-token chain in a fixed order: class_embedding, [positional_embedding], ln_pre.{weight,
+        bias}, per block ln_1.{w,b}, in_proj.{w,b}, out_proj.{w,b}, ln_2.{w,b}, c_fc.{w,b}, c_proj.{w,b}, then the
+        aug_query vectors. (ln_post and the task projections belong to the tail.)"""
+        out = [self.class_embedding]
+        if self.positional_embedding is not None:
+            out.append(self.positional_embedding)
+        out += [self.ln_pre.weight, self.ln_pre.bias]
+        for blk in self.transformer.resblocks:
+            out += [blk.ln_1.weight, blk.ln_1.bias, blk.attn.in_proj.weight, blk.attn.in_proj.bias,
+                    blk.attn.out_proj.weight, blk.attn.out_proj.bias, blk.ln_2.weight, blk.ln_2.bias,
+                    blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.c_proj.weight, blk.mlp.c_proj.bias]
+        out += list(self.transformer.augment_query_embeddings)
+        return out
+
+    def _weights_struct(self, tensors, ln_post=(None, None)):
+        """``dfd_decoder_weights`` over ``tensors`` (``_chain_params`` order: the parameters themselves, or gradient
+        buffers of their shapes). Returns (struct, objects to keep alive while the struct is in use)."""
+        for ten in tensors:
+            if ten.device.type != "cuda" or ten.dtype != torch.float32 or not ten.is_contiguous():
+                raise _native.NativeError("decoder parameters must be contiguous fp32 CUDA tensors "
+                                          "(dfdclip_b200 has no CPU path; call .to('cuda') / .float())")
+        it = iter(tensors)
+        w = _native.DecoderWeights()
+        keep = []
+        w.class_embedding = next(it).data_ptr()
+        w.positional_embedding = None if self.positional_embedding is None else next(it).data_ptr()
+        w.ln_pre_weight, w.ln_pre_bias = next(it).data_ptr(), next(it).data_ptr()
+        w.ln_post_weight = None if ln_post[0] is None else ln_post[0].data_ptr()
+        w.ln_post_bias = None if ln_post[1] is None else ln_post[1].data_ptr()
+        nb = len(self.transformer.resblocks)
+        per_block = [[next(it) for _ in range(12)] for _ in range(nb)]
+        fields = ("ln_1_weight", "ln_1_bias", "in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias",
+                  "ln_2_weight", "ln_2_bias", "c_fc_weight", "c_fc_bias", "c_proj_weight", "c_proj_bias")
+        for j, name in enumerate(fields):
+            a = _native.ptr_array([blk[j] for blk in per_block])
+            keep.append(a)
+            setattr(w, name, ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p)))
+        aug = list(it)
+        if aug:
+            a = _native.ptr_array(aug)
+            keep.append(a)
+            w.augment_query = ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p))
+        else:
+            w.augment_query = None
+        w.attn_mode = self.attn_mode
+        return w, keep
+
     def _native_weights(self):
         """``dfd_decoder_weights`` struct of fp32 device pointers (parameters are used in place, not copied)."""
         params = list(self.parameters())
         key = tuple((p.data_ptr(), str(p.device), p.dtype) for p in params)
         if self._wcache is not None and self._wcache[0] == key:
             return self._wcache[1]
-        for p in params:
-            if p.device.type != "cuda" or p.dtype != torch.float32 or not p.is_contiguous():
-                raise _native.NativeError("decoder parameters must be contiguous fp32 CUDA tensors "
-                                          "(dfdclip_b200 has no CPU path; call .to('cuda') / .float())")
-        blocks = self.transformer.resblocks
-        w = _native.DecoderWeights()
-        keep = []
-
-        def arr(getter):
-            a = _native.ptr_array([getter(b) for b in blocks])
-            keep.append(a)
-            return ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p))
-
-        w.class_embedding = self.class_embedding.data_ptr()
-        w.positional_embedding = None if self.positional_embedding is None else self.positional_embedding.data_ptr()
-        w.ln_pre_weight, w.ln_pre_bias = self.ln_pre.weight.data_ptr(), self.ln_pre.bias.data_ptr()
-        w.ln_post_weight, w.ln_post_bias = self.ln_post.weight.data_ptr(), self.ln_post.bias.data_ptr()
-        w.ln_1_weight, w.ln_1_bias = arr(lambda b: b.ln_1.weight), arr(lambda b: b.ln_1.bias)
-        w.in_proj_weight, w.in_proj_bias = arr(lambda b: b.attn.in_proj.weight), arr(lambda b: b.attn.in_proj.bias)
-        w.out_proj_weight, w.out_proj_bias = arr(lambda b: b.attn.out_proj.weight), arr(lambda b: b.attn.out_proj.bias)
-        w.ln_2_weight, w.ln_2_bias = arr(lambda b: b.ln_2.weight), arr(lambda b: b.ln_2.bias)
-        w.c_fc_weight, w.c_fc_bias = arr(lambda b: b.mlp.c_fc.weight), arr(lambda b: b.mlp.c_fc.bias)
-        w.c_proj_weight, w.c_proj_bias = arr(lambda b: b.mlp.c_proj.weight), arr(lambda b: b.mlp.c_proj.bias)
-        aug = self.transformer.augment_query_embeddings
-        if aug:
-            a = _native.ptr_array(list(aug))
-            keep.append(a)
-            w.augment_query = ctypes.cast(a, ctypes.POINTER(ctypes.c_void_p))
-        else:
-            w.augment_query = None
-        w.attn_mode = self.attn_mode
+        w, keep = self._weights_struct(self._chain_params(), (self.ln_post.weight, self.ln_post.bias))
         self._wcache = (key, w, keep)
         return w
 
@@ -251,29 +346,40 @@ class Decoder(nn.Module):
         return self.run(kvs, m, logit_scale=0.0)
 
     def run_autograd(self, kvs, m, logit_scale=0.0):
-        """Differentiable ``run`` for the training step (reference :568-596 with ``train=True``): the K/V-streaming
-        attention uses the native forward/backward kernels; the one-token-per-clip LayerNorm / linear layers are
-        evaluated with torch ops in fp32 so that autograd produces the parameter gradients (SGD step, DDP
-        all-reduce) exactly as in the reference's trainer. Gradients never reach the frozen encoder."""
+        """Differentiable ``run`` for the training step (reference :568-596 with ``train=True``). Default: the whole
+        one-token chain is ONE autograd node with native forward and hand-written native backward
+        (``_DecoderChainFn``), the tail (ln_post, projections, normalisation) a few torch ops on ``[B, D]``. With a
+        trainable adapter on the taps, ``op_mode.attn_mode`` or active dropout the chain's LayerNorm / linear layers run
+        as torch fp32 modules around the attention (native forward / backward, or torch ops for ``attn_mode``).
+        Gradients never reach the frozen encoder."""
         k0 = kvs[0]["k"]
         b, t, p = k0.shape[:3]
         h, d = self.heads, self.width
         if k0.device.type != "cuda":
             raise _native.NativeError("dfdclip_b200 decoder needs CUDA tensors (no CPU fallback)")
-        if self.attn_mode:
-            raise NotImplementedError("the training step (decoder backward) is implemented for the default "
-                                      "op_mode.attn_mode only")
-        x = self.drop_pre(self.ln_pre(self.class_embedding.view(1, d)).expand(b, d))
-        aug = self.transformer.augment_query_embeddings
-        outs = []
-        for i, (blk, kv) in enumerate(zip(self.transformer.resblocks, kvs)):
-            qs = blk.attn.in_proj(blk.ln_1(x)).view(b, h, 128)
-            mix = _DecoderAttentionFn.apply(qs, self.positional_embedding, kv["k"], kv["v"], m)
-            x = x + blk.attn.out_proj(mix)
-            x = x + blk.mlp(blk.ln_2(x))
-            outs.append(x)
-            if aug and i + 1 < len(kvs):
-                x = x + aug[i]
+        kv_grad = any(kv[n].requires_grad for kv in kvs for n in ("k", "v"))
+        if not kv_grad and not self.attn_mode and not (self.training and self.dropout > 0) and \
+                os.environ.get("DFD_NATIVE_DECODER_BWD", "1") != "0":
+            # frozen taps, no active dropout: the whole chain is one native forward / backward node
+            stack = _DecoderChainFn.apply(self, kvs, m, *self._chain_params())
+            outs = list(stack.unbind(dim=1))
+        else:
+            # trainable adapter on the taps (dK / dV needed), op_mode.attn_mode or active dropout: torch modules around
+            # the attention
+            x = self.drop_pre(self.ln_pre(self.class_embedding.view(1, d)).expand(b, d))
+            aug = self.transformer.augment_query_embeddings
+            outs = []
+            for i, (blk, kv) in enumerate(zip(self.transformer.resblocks, kvs)):
+                qs = blk.attn.in_proj(blk.ln_1(x)).view(b, h, 128)
+                if self.attn_mode:
+                    mix = _mode_attention_autograd(qs, self.positional_embedding, kv["k"], kv["v"], m, self.attn_mode)
+                else:
+                    mix = _DecoderAttentionFn.apply(qs, self.positional_embedding, kv["k"], kv["v"], m)
+                x = x + blk.attn.out_proj(mix)
+                x = x + blk.mlp(blk.ln_2(x))
+                outs.append(x)
+                if aug and i + 1 < len(kvs):
+                    x = x + aug[i]
         if self.global_prediction:
             video_feature = self.drop_post(self.ln_post(torch.stack(outs, dim=1)))  # [B, n_blocks, D] (:340-343)
         else:
@@ -853,3 +959,9 @@ class Detector(nn.Module):
         import torchvision.transforms as T
         n_px = self.encoder.input_resolution
         return T.Compose([T.Resize(n_px, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(n_px)])
+
+    def transform_device(self, frames):
+        """The whole loader transform's geometry on the GPU: raw uint8 frames ``[..., 3, H, W]`` of any size (device
+        tensors) -> uint8 ``[..., 3, R, R]`` = ``transform_uint8`` within 1 LSB (``dfd_resize_crop_u8``). ``predict`` /
+        ``forward`` / ``encoder`` also take such frames directly and call this themselves."""
+        return _native.resize_crop_u8(frames, self.encoder.input_resolution, self.encoder._resize_workspace)

@@ -1,77 +1,150 @@
 """Training-step driver for BASELINE config C5 (frozen encoder, trainable decoder / adapter): the body of the
-reference's trainer loop — ``Detector.forward(train=True)``, ``loss.backward()``, ``optimizer.step()``
-(src/trainer.py:147-178) — captured ONCE into a CUDA graph and replayed per batch.
+reference's trainer loop — ``Detector.forward(train=True)``, ``loss.backward()``, gradient all-reduce across the ranks
+(the DDP wrap of main.py:283-287 / src/trainer.py:73), ``optimizer.step()`` (src/trainer.py:147-178) — captured ONCE
+into a CUDA graph and replayed per batch.
 
-Why: at the reference's 12 clips per GPU the native encoder needs 3.2 ms, while the one-token-per-clip decoder under
-torch autograd plus the optimizer step is ~300 small launches whose cost is host dispatch, not GPU time (measured
-6.1 ms per eager step on a B200). A replayed graph has no per-launch host cost.
+Why a graph: at the reference's 12 clips per GPU the native encoder needs ~3.2 ms while the decoder's forward /
+backward is a few hundred small launches whose cost is host dispatch, not GPU time. A replayed graph has no per-launch
+host cost, also with the NCCL all-reduce inside (eager DDP measured 9.3 ms per step on 8 GPUs in round 1, host bound).
 
-The step computes exactly what the eager sequence computes (same kernels in the same order on the same buffers);
-``tests/test_train_gpu.py::test_graphed_train_step_matches_eager_steps`` pins it against eager steps.
+Gradients live in ONE flat fp32 buffer (``.grad`` of every trainable parameter is a view into it): the native decoder
+backward writes the chain's gradients straight into it (``Decoder._grad_sink``), the all-reduce is a single NCCL call
+on the buffer (average, as DDP), and the fused SGD kernel reads it. The step computes what the eager sequence computes;
+``tests/test_train_gpu.py`` pins it against eager steps and against the oracle's autograd.
 """
 import torch
 
 
-class GraphedTrainStep:
-    """``step = GraphedTrainStep(detector, optimizer, x, y, m)`` then ``loss, logits = step(x, y, m)`` per batch.
+class TrainStep:
+    """``step = TrainStep(detector, optimizer, x, y, m, group=None)`` then ``loss, logits = step(x, y, m)`` per batch.
 
     * ``x`` fp32 (normalised) or uint8 ``[B,T,3,R,R]``, ``y`` int64 ``[B]`` (labels of task ``single_task``), ``m`` bool
       ``[B,T]`` — device tensors; every later batch must have the shapes / dtypes of the example batch (the reference
-      trains with ``drop_last`` fixed-size batches, src/datasets.py loaders via main.py:246-262).
-    * The example batch is used for warm-up (optimizer state creation, allocator warm-up, lazy kernel attributes); the
-      parameters are restored and the optimizer state zeroed afterwards, so constructing the step does not train.
+      trains with fixed-size batches, main.py:246-262).
+    * ``group``: a ``torch.distributed`` process group (NCCL) — every rank runs the same step on its own batch and the
+      gradients are averaged across the group inside the captured step (what DDP does for the reference); None = one GPU.
+    * The example batch is used for warm-up (optimizer state creation, allocator warm-up, lazy kernel attributes,
+      NCCL connection set-up); parameters, module buffers and optimizer state are restored afterwards, so constructing
+      the step does not train.
+    * Learning-rate schedules: the step keeps ``lr`` in a device tensor that the captured optimizer kernel reads;
+      call ``step.set_lr(value)`` (or ``step.sync_lr(scheduler)``) before a replay — the reference calls
+      ``OneCycleLR.step()`` after every optimizer step (src/trainer.py:175-176). A momentum that changes between steps
+      (``OneCycleLR(cycle_momentum=True)``) cannot be replayed and raises.
     * ``loss`` (scalar: mean task loss + auxiliary losses) and ``logits`` are views of static buffers that the next call
       overwrites.
-    * Not supported (raise): ``train_mode.patch_mask`` (its patch indices are drawn on the host with numpy for every
-      step, reference :511-544) and anything that needs a host decision inside the step. Gradient all-reduce for
-      multi-GPU training is not part of the captured step.
+    * Not capturable (raise up front): ``train_mode.patch_mask`` (patch indices drawn on the host with numpy per step,
+      reference :511-544), ``train_mode.temporal`` (host-side argsort / shuffle, :676-736) and class-weighted losses
+      (a host list turned into a tensor inside the loss, :36-37). Use ``graph=False`` (eager body, same arithmetic).
     """
 
-    def __init__(self, detector, optimizer, x, y, m, single_task=0, speed=None, warmup=2):
-        if "patch_mask" in detector.train_mode:
-            raise NotImplementedError("train_mode.patch_mask draws patch indices on the host for every step: "
-                                      "it cannot be replayed from a CUDA graph; use the eager step")
+    def __init__(self, detector, optimizer, x, y, m, single_task=0, speed=None, group=None, warmup=2, graph=True):
         dev = x.device
         if dev.type != "cuda":
-            raise RuntimeError("GraphedTrainStep needs CUDA tensors (dfdclip_b200 has no CPU path)")
-        self.det, self.opt, self.task = detector, optimizer, int(single_task)
+            raise RuntimeError("TrainStep needs CUDA tensors (dfdclip_b200 has no CPU path)")
+        if graph:
+            for key in ("patch_mask", "temporal"):
+                if key in detector.train_mode:
+                    raise NotImplementedError("train_mode.%s needs host work inside every step: it cannot be replayed "
+                                              "from a CUDA graph; use TrainStep(..., graph=False)" % key)
+            for loss in detector.config.losses:
+                args = {} if isinstance(loss, str) or "args" not in loss else dict(loss.args)
+                if args.get("weight"):
+                    raise NotImplementedError("a class-weighted loss builds its weight tensor on the host in every "
+                                              "step: not capturable; use TrainStep(..., graph=False)")
+        self.det, self.opt, self.task, self.dev = detector, optimizer, int(single_task), dev
+        self.group = group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self.dist = dist
+            self.world = dist.get_world_size(group)
         self.x, self.y, self.m = x.clone(), y.clone(), m.clone()
         self.speed = None if speed is None else speed.clone()
-        params = [p for g in optimizer.param_groups for p in g["params"]]
-        saved = [p.detach().clone() for p in params]
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
+        self.params = [p for g in optimizer.param_groups for p in g["params"]]
+        self._build_flat_gradients()
+        # lr as a device tensor: the captured fused-SGD kernel reads it at replay time
+        self._lr = []
+        for g in optimizer.param_groups:
+            if not torch.is_tensor(g["lr"]):
+                g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev)
+            self._lr.append(g["lr"])
+        self._frozen_hyper = [self._hyper(g) for g in optimizer.param_groups]
+        taps, nb = detector.layer_indices, len(detector.layer_indices)
+        # kernels of this library per step: encoder (stem 4, 7 per full layer, 2 for the last tap's LayerNorm + K/V
+        # projection), decoder chain forward (1 + 12 per block) and backward (19 per block, 2 more between blocks, 3 at
+        # the end); the tail / loss / SGD are ~30 torch kernels more
+        self.launches_per_step = (4 + 7 * max(taps) + 2) + (1 + 12 * nb) + (19 * nb + 2 * (nb - 1) + 3)
+        self.graph = None
+        self._warm_up(max(1, int(warmup)))
+        if graph:
+            self.graph = torch.cuda.CUDAGraph()
+            # thread_local: other threads (NVML sampling, NCCL's watchdog) may touch CUDA while this one captures
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.loss, self.logits = self._body()
+
+    # ------------------------------------------------------------------------------------------ set-up
+    @staticmethod
+    def _hyper(group):
+        return tuple((k, group[k]) for k in ("momentum", "weight_decay", "dampening", "nesterov", "betas", "eps")
+                     if k in group)
+
+    def _build_flat_gradients(self):
+        """One fp32 buffer for all gradients; ``p.grad`` = view. Chain parameters of the decoder get their gradient
+        written in place by the native backward (``_grad_sink``); the few tail parameters (ln_post, projections, ...)
+        are accumulated by autograd into their (zeroed) views."""
+        offs, total = [], 0
+        for p in self.params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("TrainStep expects contiguous fp32 parameters")
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        for p, o in zip(self.params, offs):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        chain = {id(p) for p in self.det.decoder._chain_params()}
+        self.det.decoder._grad_sink = {id(p): p.grad for p in self.params if id(p) in chain}
+        self._tail = [p for p in self.params if id(p) not in chain]
+
+    def _warm_up(self, n):
+        opt, det = self.opt, self.det
+        saved = [p.detach().clone() for p in self.params]
+        buffers = [(b, b.detach().clone()) for b in det.buffers()]   # e.g. BatchNorm statistics of a 768-bn adapter
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
-            for _ in range(max(1, int(warmup))):
-                optimizer.zero_grad(set_to_none=True)
+            for _ in range(n):
                 self._body()
-            # undo the warm-up: parameters back, optimizer state as freshly created (zero momentum / moments / step)
+            # undo the warm-up: parameters and buffers back, optimizer state as freshly created
             with torch.no_grad():
-                for p, s in zip(params, saved):
+                for p, s in zip(self.params, saved):
                     p.copy_(s)
-                for state in optimizer.state.values():
+                for b, s in buffers:
+                    b.copy_(s)
+                for state in opt.state.values():
                     for v in state.values():
                         if torch.is_tensor(v):
                             v.zero_()
-            optimizer.zero_grad(set_to_none=True)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.logits = self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
 
+    # ------------------------------------------------------------------------------------------ the step
     def _body(self):
         with torch.enable_grad():
+            for p in self._tail:          # autograd ACCUMULATES into existing .grad tensors
+                p.grad.zero_()
             losses, logits, other = self.det(self.x, [self.y] * (self.task + 1), self.m, speed=self.speed, train=True,
                                              single_task=self.task)
             loss = losses[self.task].mean()
             for v in other.values():
                 loss = loss + v
             loss.backward()
+        if self.world > 1:
+            # DDP's gradient averaging as ONE collective on the flat buffer (NCCL over NVLink, captured in the graph)
+            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG, group=self.group)
         self.opt.step()
         return loss.detach(), logits[self.task].detach()
 
-    def __call__(self, x, y, m, speed=None):
+    def _load(self, x, y, m, speed):
         if x.shape != self.x.shape or x.dtype != self.x.dtype or y.shape != self.y.shape or m.shape != self.m.shape:
             raise ValueError("batch %s/%s/%s does not match the captured step %s/%s/%s" % (
                 tuple(x.shape), tuple(y.shape), tuple(m.shape), tuple(self.x.shape), tuple(self.y.shape),
@@ -83,5 +156,45 @@ class GraphedTrainStep:
             if speed is None:
                 raise ValueError("the captured step takes a `speed` tensor")
             self.speed.copy_(speed, non_blocking=True)
-        self.graph.replay()
+        for g, frozen in zip(self.opt.param_groups, self._frozen_hyper):
+            if self.graph is not None and self._hyper(g) != frozen:
+                raise RuntimeError("optimizer hyper-parameters changed since the step was captured (%s -> %s): a "
+                                   "replayed graph would ignore them (e.g. OneCycleLR(cycle_momentum=True)); re-create "
+                                   "the TrainStep or disable the cycling" % (dict(frozen), dict(self._hyper(g))))
+
+    def set_lr(self, lr):
+        """Set the learning rate(s) the next steps use: one value for all parameter groups or one per group."""
+        values = [lr] * len(self._lr) if not isinstance(lr, (list, tuple)) else list(lr)
+        for t, g, v in zip(self._lr, self.opt.param_groups, values):
+            t.fill_(float(v))
+            g["lr"] = t      # a scheduler may have replaced the tensor by a float
+
+    def sync_lr(self, scheduler):
+        """After ``scheduler.step()``: copy the scheduler's current learning rates into the captured step."""
+        self.set_lr([float(v) for v in scheduler.get_last_lr()])
+
+    def __call__(self, x, y, m, speed=None):
+        self._load(x, y, m, speed)
+        if self.graph is None:
+            self.loss, self.logits = self._body()
+        else:
+            self.graph.replay()
         return self.loss, self.logits
+
+    def eager(self, x, y, m, speed=None):
+        """The same step without the graph (per-kernel timing, debugging)."""
+        self._load(x, y, m, speed)
+        return self._body()
+
+    def describe(self):
+        return ("Detector.forward(train=True) + backward + %sfused SGD, %s; native encoder, native decoder chain "
+                "forward/backward (dfd_decoder_train_*), gradients in one flat fp32 buffer" % (
+                    "all_reduce(AVG) over %d ranks + " % self.world if self.world > 1 else "",
+                    "one CUDA graph replay per step" if self.graph is not None else "eager"))
+
+
+class GraphedTrainStep(TrainStep):
+    """Single-GPU ``TrainStep`` under its round-1 name."""
+
+    def __init__(self, detector, optimizer, x, y, m, single_task=0, speed=None, warmup=2):
+        super().__init__(detector, optimizer, x, y, m, single_task=single_task, speed=speed, group=None, warmup=warmup)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DFD_ABI_VERSION 2
+#define DFD_ABI_VERSION 3
 
 enum {
   DFD_OK = 0,
@@ -332,6 +332,50 @@ int dfd_decoder_attention_backward(dfd_ctx* ctx, const float* qs, const void* k,
                                    const float* stats, const float* dmix, int B, int T, int P, int H, float* dqs,
                                    float* dpos_emb, float* dk, float* dv, void* workspace, size_t workspace_bytes,
                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Input side: the data loader's T.Resize(n_px, BICUBIC) + T.CenterCrop(n_px) (src/models.py:756-761; applied to the
+ * stacked uint8 frames at src/datasets.py:672-676) on the device. frames: uint8 [n_frames, 3, H, W] of any size;
+ * out: uint8 [n_frames, 3, R, R]. torchvision's tensor path: the smaller edge is resized to R (the other keeps the
+ * aspect ratio), antialiased separable bicubic interpolation in fp32 (Keys a = -0.5, support 2 * max(scale, 1),
+ * normalised weights, width pass first), clamp to [0, 255], round half to even, then the centre crop — reproduced
+ * within 1 LSB (fp32 summation order). The remaining transform steps (ConvertImageDtype + Normalize) are fused into
+ * dfd_patchify_u8 / dfd_encoder_forward_u8. */
+size_t dfd_resize_crop_u8_workspace_bytes(int n_frames, int H, int W, int R);
+int dfd_resize_crop_u8(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, int R, uint8_t* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Training step of the decoder (BASELINE config C5). Replaces, inside the reference trainer's
+ * forward(train=True) -> backward (src/trainer.py:147-165), the autograd graph of Decoder.forward's chain
+ * (src/models.py:336-338, 259-269, 173-176, 136-146: ln_pre(class_embedding), then per block ln_1 -> in_proj ->
+ * attention -> out_proj -> residual -> ln_2 -> c_fc -> QuickGELU -> c_proj -> residual, aug_query between blocks).
+ * ln_post, the task projection(s), the logit normalisation and the loss stay with the caller.
+ *
+ * dfd_decoder_train_forward: block_out fp32 [B, n_blocks, D] as dfd_decoder_forward, activations kept in `saved`
+ * (dfd_decoder_train_bytes; the same buffer must be handed to the backward untouched).
+ * dfd_decoder_train_backward: given d_block_out fp32 [B, n_blocks, D], writes the gradient of every parameter of the
+ * chain through `grads` — a dfd_decoder_weights whose pointers are OUTPUT buffers of the parameters' shapes
+ * (class_embedding, positional_embedding [summed over the blocks], ln_pre_*, per block ln_1_*, in_proj_*, out_proj_*,
+ * ln_2_*, c_fc_*, c_proj_*, augment_query; ln_post_* and attn_mode are ignored). dk / dv: NULL, or HOST arrays of
+ * n_blocks device pointers to contiguous fp32 [B, T, P, H, 64] buffers for the gradients w.r.t. the tapped K / V (a
+ * trainable adapter on the taps). op_mode.attn_mode != 0 is rejected. fp32 throughout, deterministic. */
+size_t dfd_decoder_train_bytes(int B, int T, int D, int n_blocks);
+int dfd_decoder_train_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
+                              const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
+                              void* saved, size_t saved_bytes, void* stream);
+int dfd_decoder_train_backward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
+                               const dfd_decoder_weights* grads, const dfd_kv_taps* taps, const uint8_t* mask, int B,
+                               int T, int P, const float* d_block_out, float* const* dk, float* const* dv, void* saved,
+                               size_t saved_bytes, void* stream);
+
+/* Backward of one of the decoder's nn.Linear layers (dfd_linear_f32), exported for unit tests:
+ * dx[b,k] = (sum_n dy[b,n] W[n,k]) * quickgelu'(gelu_pre[b,k]) + dx_add[b,k];  dW[n,k] = sum_b dy[b,n] x[b,k];
+ * db[n] = sum_b dy[b,n]. gelu_pre / dx_add / dx / dW / db may be NULL (db is only written together with dW). */
+size_t dfd_linear_f32_backward_workspace_bytes(int B, int N, int K);
+int dfd_linear_f32_backward(dfd_ctx* ctx, const float* x, const float* W, const float* dy, const float* gelu_pre,
+                            const float* dx_add, float* dx, float* dW, float* db, int B, int N, int K, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,17 +70,22 @@ def predict_chunked(det, x, m, sample_taps=False, seeds=None):
 
 
 def centred_head(features, width, seed=0):
-    """A [D, 2] task head whose class margin straddles zero on `features`: columns c + d and c - d with the difference
-    direction d orthogonal to the mean feature, scaled so that the margins of the normalised logits have a standard
-    deviation of about 1 (logits are rescaled to norm 5, src/models.py:551-553)."""
+    """A [D, 2] task head whose class margin straddles zero on `features`: columns c + d and c - d with
+      * the common direction c along the mean feature mu (c.f ~ 1 for every clip: the raw logits keep a healthy norm,
+        as a trained head's do. With a random c the common part changes sign from clip to clip and 5 l / |l|
+        (src/models.py:551-553) divides by almost nothing there: the normalised logits of such clips are
+        ill-conditioned for ANY finite-precision evaluation, the reference's own included), and
+      * the difference direction d orthogonal to mu, scaled so that the margins of the normalised logits have a
+        standard deviation of about 1: both classes occur and near ties (|margin| < 0.05) are likely among 64 clips."""
     g = torch.Generator().manual_seed(1000 + seed)
-    mu = features.double().mean(0)
-    c = torch.randn(width, generator=g, dtype=torch.float64) * width ** -0.5
+    f = features.double()
+    mu = f.mean(0)
+    c = mu / (mu @ mu)
     d = torch.randn(width, generator=g, dtype=torch.float64) * width ** -0.5
     d = d - (d @ mu) / (mu @ mu) * mu
-    common = (features.double() @ c).abs().mean()
-    spread = (features.double() @ d).std()
-    d = d * (common / spread) * (1.0 / 5.0) * 2 ** -0.5     # margin = 5 * 2 d.f / (sqrt(2) |c.f|) ~ N(0, 1)
+    common = (f @ c).abs().mean()
+    spread = (f @ d).std()
+    d = d * (common / spread) * (1.0 / 5.0) * 2 ** -0.5     # margin ~ 5 sqrt(2) d.f / c.f ~ N(0, 1)
     return torch.stack([c + d, c - d], dim=1).float()
 
 
@@ -115,7 +120,11 @@ def case_c2():
     x, m = synthetic.make_varied_clips(b, t, 224, seed=7)
     det = build_reference_detector(arch, t)
     t0 = time.time()
-    _, feats, _ = predict_chunked(det, x, m)
+    prev = os.path.join(GOLDEN_DIR, "reference_vitb16_c2.npz")
+    if os.path.exists(prev) and os.environ.get("DFD_GOLDEN_REUSE_FEATURES", "1") == "1":
+        feats = torch.from_numpy(np.load(prev)["video_feature"])  # the features do not depend on the head
+    else:
+        _, feats, _ = predict_chunked(det, x, m)
     print("c2 pass 1 (features for the head) %.0f s" % (time.time() - t0), flush=True)
     proj = centred_head(feats, 768)
     det.decoder.proj0x2.data.copy_(proj)

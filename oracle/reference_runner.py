@@ -56,7 +56,8 @@ def build_reference_detector(arch, num_frames, proj=None, root=None):
     cfg.out_dim = [2]
     cfg.losses = ["auc_roc"]
     torch.manual_seed(1)
-    det = Detector(cfg, num_frames, gg.FakeAccelerator())
+    # the reference's clip.load defaults to device="cuda" when one is visible (src/clip/clip.py:94): this is the CPU arm
+    det = Detector(cfg, num_frames, gg.FakeAccelerator()).to("cpu")
     os.remove(ckpt)
     os.rmdir(tmp)
     sd = synthetic.detector_state_dict(arch, num_frames, out_dims=(2,), taps=det.layer_indices, seed=0)

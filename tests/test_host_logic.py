@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "libdfdclip_b200.so does not export " + name
     assert declared == set(nat.EXPORTS), (declared ^ set(nat.EXPORTS))
-    assert lib.dfd_version() == 2
+    assert lib.dfd_version() == 3
 
 
 def test_native_refuses_without_gpu():

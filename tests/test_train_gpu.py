@@ -302,3 +302,177 @@ def test_graphed_train_step_matches_eager_steps(cuda_device, u8):
     assert moved >= 30
     with pytest.raises(ValueError):
         step(batches[0][0][:2], batches[0][1][:2], batches[0][2][:2])
+
+
+# ------------------------------------------------------------------------- native decoder backward (dfd_decoder_train_*)
+@pytest.mark.parametrize("b,n,k", [(12, 1536, 768), (12, 768, 3072), (3, 256, 256), (33, 3072, 768), (1, 768, 768)])
+@pytest.mark.parametrize("gelu,add", [(False, False), (True, True)])
+def test_linear_f32_backward(cuda_device, b, n, k, gelu, add):
+    """dX = dY W (* quickgelu'(pre)) (+ add), dW = dY^T X, db = sum_b dY of one decoder nn.Linear against torch autograd."""
+    from dfdclip_b200 import _native as nat
+    g = torch.Generator(device="cpu").manual_seed(b + n + k)
+    x = torch.randn(b, k, generator=g).to(cuda_device)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(cuda_device)
+    dy = torch.randn(b, n, generator=g).to(cuda_device)
+    pre = torch.randn(b, k, generator=g).to(cuda_device) if gelu else None
+    extra = torch.randn(b, k, generator=g).to(cuda_device) if add else None
+    dx, dw, db = nat.linear_f32_backward(x, w, dy, gelu_pre=pre, dx_add=extra)
+    torch.cuda.synchronize()
+    ref_dx = dy.double() @ w.double()
+    if gelu:  # x here is quickgelu(pre) in the chain; the kernel only needs pre for the derivative
+        p = pre.double().requires_grad_(True)
+        (p * torch.sigmoid(1.702 * p)).backward(ref_dx)
+        ref_dx = p.grad
+    if add:
+        ref_dx = ref_dx + extra.double()
+    ref_dw = dy.double().t() @ x.double()
+    assert (dx.double() - ref_dx).abs().max().item() < 1e-4 * max(1.0, ref_dx.abs().max().item())
+    assert (dw.double() - ref_dw).abs().max().item() < 1e-4 * max(1.0, ref_dw.abs().max().item())
+    assert (db.double() - dy.double().sum(0)).abs().max().item() < 1e-4
+    only_dx, none_w, none_b = nat.linear_f32_backward(x, w, dy, gelu_pre=pre, dx_add=extra, need_dw=False)
+    assert torch.equal(only_dx, dx) and none_w is None and none_b is None
+
+
+def _build_small_detector(device, op_mode=None, arch="small-512x6", frames=3):
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.models import Detector
+    cfg = Detector.get_default_config()
+    cfg.architecture = "synthetic:" + arch
+    cfg.out_dim = [2]
+    cfg.losses = ["auc_roc"]
+    for key, val in (op_mode or {}).items():
+        cfg.op_mode[key] = val
+    det = Detector(cfg, frames, None)
+    op = op_mode or {}
+    sd = synthetic.detector_state_dict(arch, frames, out_dims=(2,), taps=det.layer_indices, seed=0,
+                                       aug_query=bool(op.get("aug_query")),
+                                       global_prediction=bool(op.get("global_prediction")),
+                                       temporal_position=bool(op.get("temporal_position", 1)))
+    det.load_state_dict(sd, strict=True)
+    return det.to(device).train(), sd
+
+
+@pytest.mark.parametrize("op_mode", [None, {"aug_query": 1}, {"global_prediction": 1, "aug_query": 1},
+                                     {"temporal_position": 0}])
+def test_native_decoder_chain_backward_matches_the_torch_module_path(cuda_device, monkeypatch, op_mode):
+    """The one-node native chain (dfd_decoder_train_forward / _backward) against the same step with the chain's
+    LayerNorm / linear layers as torch modules under autograd (DFD_NATIVE_DECODER_BWD=0; same attention kernels):
+    loss, logits and every gradient agree to fp32 round-off, for every op_mode that changes the chain's wiring."""
+    from dfdclip_b200 import synthetic
+    det, _ = _build_small_detector(cuda_device, op_mode)
+    x, m = synthetic.make_clips(5, 3, 64, seed=21)
+    y = torch.tensor([0, 1, 1, 0, 1], device=cuda_device)
+    results = []
+    for native in ("0", "1"):
+        monkeypatch.setenv("DFD_NATIVE_DECODER_BWD", native)
+        det.zero_grad(set_to_none=True)
+        with torch.enable_grad():
+            losses, logits, _ = det(x.to(cuda_device), [y], m.to(cuda_device), train=True, single_task=0)
+            losses[0].mean().backward()
+        results.append((losses[0].detach().clone(), logits[0].detach().clone(),
+                        {n: p.grad.detach().clone() for n, p in det.named_parameters() if p.requires_grad}))
+    (l0, g0, gr0), (l1, g1, gr1) = results
+    assert (l0 - l1).abs().max().item() < 1e-5 and (g0 - g1).abs().max().item() < 1e-4
+    assert set(gr0) == set(gr1) and len(gr1) >= 40
+    for name in gr0:
+        scale = max(gr0[name].abs().max().item(), 1e-6)
+        err = (gr0[name] - gr1[name]).abs().max().item()
+        assert err < 2e-4 * scale + 1e-7, (name, err, scale)
+
+
+@pytest.mark.parametrize("mode", ["frame", "temporal+frame"])
+def test_training_step_with_attn_mode_matches_oracle(cuda_device, mode):
+    """op_mode.attn_mode in the training step (the shipped deepfake configs train with it): loss and decoder gradients
+    against the oracle's autograd. Clips without padded frames (a padded frame gives NaN in 'frame' mode, :111)."""
+    from dfdclip_b200 import synthetic
+    oracle = load_oracle()
+    det, sd = _build_small_detector(cuda_device, {"attn_mode": mode})
+    x, m = synthetic.make_clips(4, 3, 64, seed=9, masked_tail=False)
+    y = torch.tensor([1, 0, 0, 1])
+    with torch.enable_grad():
+        losses, logits, _ = det(x.to(cuda_device), [y.to(cuda_device)], m.to(cuda_device), train=True, single_task=0)
+        loss = losses[0].mean()
+        loss.backward()
+        sd_r = {k_: (v_.clone().requires_grad_(True) if k_.startswith("decoder.") else v_) for k_, v_ in sd.items()}
+        ref_logits, _ = oracle.detector_predict(sd_r, x, m, det.layer_indices, (2,), attn_mode=tuple(mode.split("+")))
+        ref_loss = oracle.detector_eval_losses(ref_logits, [y])[0].mean()
+        ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 3e-2
+    checked = 0
+    for name, p in det.decoder.named_parameters():
+        ref_g = sd_r["decoder." + name].grad
+        if ref_g is None or ref_g.abs().max().item() < 1e-7:
+            continue
+        assert cosine(p.grad.cpu(), ref_g) > 0.99, (name, cosine(p.grad.cpu(), ref_g))
+        checked += 1
+    assert checked >= 30
+
+
+def test_train_step_follows_a_learning_rate_schedule(cuda_device):
+    """The captured step reads lr from a device tensor: three replays under OneCycleLR (cycle_momentum=False, synced with
+    step.sync_lr) equal three eager steps under the same scheduler; a cycled momentum is refused instead of ignored."""
+    import copy
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.training import TrainStep
+    det_a, _ = _build_small_detector(cuda_device)
+    det_b = copy.deepcopy(det_a)
+    batches = []
+    for i in range(3):
+        x, m = synthetic.make_clips(4, 3, 64, seed=60 + i)
+        y = torch.randint(0, 2, (4,), generator=torch.Generator().manual_seed(70 + i))
+        batches.append((x.to(cuda_device), y.to(cuda_device), m.to(cuda_device)))
+    opt_a = det_a.configure_optimizers(lr=0.002)
+    sch_a = torch.optim.lr_scheduler.OneCycleLR(opt_a, max_lr=0.05, total_steps=3, cycle_momentum=False)
+    for x, y, m in batches:
+        with torch.enable_grad():
+            losses, _, _ = det_a(x, [y], m, train=True, single_task=0)
+            losses[0].mean().backward()
+        opt_a.step()
+        sch_a.step()
+        opt_a.zero_grad(set_to_none=True)
+    opt_b = det_b.configure_optimizers(lr=0.002)
+    sch_b = torch.optim.lr_scheduler.OneCycleLR(opt_b, max_lr=0.05, total_steps=3, cycle_momentum=False)
+    before = [p.detach().clone() for p in det_b.parameters()]
+    step = TrainStep(det_b, opt_b, *batches[0])
+    step.sync_lr(sch_b)
+    for x, y, m in batches:
+        step(x, y, m)
+        sch_b.step()
+        step.sync_lr(sch_b)
+    torch.cuda.synchronize()
+    for (name, p), q, p0 in zip(det_b.named_parameters(), det_a.parameters(), before):
+        if p.requires_grad:
+            delta = (q - p0).norm().item()
+            assert (p - q).norm().item() <= 2e-3 * delta + 1e-6, (name, (p - q).norm().item(), delta)
+    opt_b.param_groups[0]["momentum"] = 0.5
+    with pytest.raises(RuntimeError):
+        step(*batches[0])
+
+
+def test_captured_graphs_survive_a_larger_eager_call(cuda_device):
+    """Workspaces handed out under stream capture are never freed: a captured predict keeps replaying correctly after an
+    eager call with a bigger batch made the encoder / decoder workspaces grow."""
+    from dfdclip_b200 import synthetic
+    det, _ = _build_small_detector(cuda_device)
+    det.eval()
+    x, m = synthetic.make_clips(3, 3, 64, seed=3)
+    xs, ms = x.to(cuda_device), m.to(cuda_device)
+    with torch.no_grad():
+        ref = det.predict(xs, ms)[0][0].clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            det.predict(xs, ms)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = det.predict(xs, ms)[0][0]
+        small_ws = det.encoder._workspace.buf
+        xb, mb = synthetic.make_clips(11, 3, 64, seed=4)
+        det.predict(xb.to(cuda_device), mb.to(cuda_device))        # grows every workspace
+        assert det.encoder._workspace.buf is not small_ws and small_ws in det.encoder._workspace.retired
+        junk = [torch.randn(1 << 22, device=cuda_device) for _ in range(8)]  # would land on a freed block
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+        del junk
