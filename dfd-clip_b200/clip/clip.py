@@ -22,7 +22,7 @@ _MODELS = {
 
 def available_models() -> List[str]:
     """Names of the CLIP ViT models this loader knows. The ResNet towers and ``ViT-L/14@336px`` (577 tokens per
-    frame; the attention kernels hold a frame's keys on chip, at most 272) are not supported by the B200 path."""
+    frame; the attention kernels hold a frame's keys on chip, at most 257) are not supported by the B200 path."""
     return list(_MODELS.keys())
 
 

@@ -16,7 +16,7 @@ from torch import nn
 from .. import _native
 
 
-MAX_TOKENS_PER_FRAME = 272   # csrc/encoder.cu vit_shape: a frame's keys stay on chip in the attention kernels
+MAX_TOKENS_PER_FRAME = 257   # csrc/encoder.cu vit_shape: a frame's keys stay on chip in the attention kernels
 
 
 class LayerNorm(nn.LayerNorm):

@@ -17,9 +17,26 @@ int fail(int code, const char* fmt, ...) {
 
 void clear_error() { g_err[0] = 0; }
 
+static bool tmap_lookup(const dfd_ctx* ctx, const dfd_tmap_key& key, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lock(ctx->tmap_mutex);
+  auto it = ctx->tmap_cache.find(key);
+  if (it == ctx->tmap_cache.end()) return false;
+  *out = it->second;
+  return true;
+}
+
+static void tmap_store(const dfd_ctx* ctx, const dfd_tmap_key& key, const CUtensorMap& map) {
+  std::lock_guard<std::mutex> lock(ctx->tmap_mutex);
+  if (ctx->tmap_cache.size() >= dfd_ctx::tmap_cache_max) ctx->tmap_cache.clear();
+  ctx->tmap_cache.emplace(key, map);
+}
+
 int make_tmap_2d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes,
                  uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   if (!ctx || !ctx->encode_tiled) return fail(DFD_ERR_INVALID, "tensor map: context has no driver entry point");
+  const dfd_tmap_key key{base, cols, rows, 0, ld, 0, box_cols, box_rows,
+                         static_cast<uint32_t>(dtype) | static_cast<uint32_t>(elem_bytes) << 8 | 2u << 16 | 1u << 24};
+  if (tmap_lookup(ctx, key, out)) return 0;
   if (box_cols * elem_bytes != 128) return fail(DFD_ERR_INVALID, "tensor map: box inner extent must be 128 bytes");
   if ((ld * elem_bytes) % 16 != 0) return fail(DFD_ERR_INVALID, "tensor map: row pitch must be a multiple of 16 bytes");
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail(DFD_ERR_INVALID, "tensor map: base must be 16-byte aligned");
@@ -34,6 +51,7 @@ int make_tmap_2d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtenso
   if (r != CUDA_SUCCESS)
     return fail(DFD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)",
                 (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+  tmap_store(ctx, key, *out);
   return 0;
 }
 
@@ -49,6 +67,10 @@ int make_tmap_3d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtenso
     return fail(DFD_ERR_INVALID, "tensor map: pitches must be multiples of 16 bytes");
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail(DFD_ERR_INVALID, "tensor map: base must be 16-byte aligned");
   if (box_rows > 256) return fail(DFD_ERR_INVALID, "tensor map: box rows > 256");
+  const dfd_tmap_key key{base, cols, rows, frames, ld, frame_ld, box_cols, box_rows,
+                         static_cast<uint32_t>(dtype) | static_cast<uint32_t>(elem_bytes) << 8 | 3u << 16 |
+                             (swizzle128 ? 1u : 0u) << 24};
+  if (tmap_lookup(ctx, key, out)) return 0;
   auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ctx->encode_tiled);
   cuuint64_t dims[3] = {cols, rows, frames};
   cuuint64_t strides[2] = {ld * static_cast<uint64_t>(elem_bytes), frame_ld * static_cast<uint64_t>(elem_bytes)};
@@ -59,6 +81,7 @@ int make_tmap_3d(const dfd_ctx* ctx, CUtensorMap* out, const void* base, CUtenso
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DFD_ERR_CUDA, "cuTensorMapEncodeTiled (3d) failed with CUresult %d", (int)r);
+  tmap_store(ctx, key, *out);
   return 0;
 }
 

@@ -500,7 +500,7 @@ int mha_fwd_tc3(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, in
                        frame_ld, KP, DH));
   DFD_TRY(make_tmap_3d(ctx, &tmO, mix, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_frames, L > KP ? KP : L, D, D,
                        static_cast<uint64_t>(L) * D, 32, DH));
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64] = {};  // per device; a repeated cudaFuncSetAttribute is harmless
   if (!configured[ctx->device & 63]) {
     DFD_CUDA_OK(cudaFuncSetAttribute(mha_fwd_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DFD_CUDA_OK(cudaFuncSetAttribute(mha_fwd_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

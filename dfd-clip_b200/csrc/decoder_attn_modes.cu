@@ -168,7 +168,7 @@ int decoder_attention_modes(const dfd_ctx* ctx, const float* qs, const void* k, 
   dec_scores_kernel<<<static_cast<unsigned>((keys + 7) / 8), 256, 0, stream>>>(
       qs, static_cast<const __nv_bfloat16*>(k), stride_b, stride_t, stride_p, pos_emb, mask, B, T, P, H, s0, a1);
   DFD_CUDA_OK(cudaGetLastError());
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64] = {};  // per device; a repeated cudaFuncSetAttribute is harmless
   if (!configured[ctx->device & 63]) {
     DFD_CUDA_OK(cudaFuncSetAttribute(dec_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured[ctx->device & 63] = true;

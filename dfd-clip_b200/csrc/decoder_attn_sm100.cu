@@ -344,7 +344,7 @@ static int launch_das(const dfd_ctx* ctx, const float* qs, const __nv_bfloat16* 
                       int64_t stride_b, int64_t stride_t, int64_t stride_p, const float* pos_emb, const uint8_t* mask,
                       int B, int T, int P, float* part, cudaStream_t stream) {
   using C = DasCfg<H, KS>;
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64] = {};  // per device; a repeated cudaFuncSetAttribute is harmless
   if (!configured[ctx->device & 63]) {
     DFD_CUDA_OK(cudaFuncSetAttribute(dec_attn_stream_kernel<H, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));

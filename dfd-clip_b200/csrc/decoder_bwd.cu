@@ -212,7 +212,7 @@ int decoder_attention_backward(const dfd_ctx* ctx, const float* qs, const void* 
 #define DFD_LAUNCH_BWD(HH, KSV)                                                                                  \
   do {                                                                                                           \
     const size_t smem = static_cast<size_t>(KSV) * HH * DBW_REC * sizeof(float);                                 \
-    static bool configured = false;                                                                              \
+    static std::atomic<bool> configured{false};                                                                        \
     if (!configured) {                                                                                           \
       DFD_CUDA_OK(cudaFuncSetAttribute(dec_attn_bwd_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                        (int)smem));                                                              \

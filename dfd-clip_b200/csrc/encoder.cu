@@ -66,7 +66,7 @@ static int vit_shape(const dfd_vit_dims* d, VitShape* s) {
   s->L = s->P + 1;
   s->K = 3 * s->p * s->p;
   s->Kp = (s->K + 63) & ~63;
-  DFD_CHECK_ARG(s->L <= 272, "encoder: %d tokens per frame exceed the attention kernel's limit of 272", s->L);
+  DFD_CHECK_ARG(s->L <= 257, "encoder: %d tokens per frame exceed the attention kernels' limit of 257", s->L);
   return 0;
 }
 

@@ -39,6 +39,105 @@ constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;  // + slack for manual 1024
 constexpr uint32_t TMEM_COLS = 512;
 }  // namespace gemm
 
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue shared by the 1-SM and the SM-pair kernel: one warp drains `box_count` boxes (32 rows x 128 bytes of
+// output each: 64 bf16 or 32 fp32 columns) of its TMEM lane quarter, starting at box `box_begin` of the tile.
+//   tcgen05.ld -> bias / LayerNorm fold / QuickGELU / erf-GELU -> 128-byte-swizzled smem box -> TMA store or reduce-add
+// `release()` is called by every lane once the warp's last TMEM read has completed (the accumulator can be reused).
+namespace gemm_epi {
+constexpr int OUT_BUF = 32 * 128;
+constexpr int OUT_BUFS_PER_WARP = 2;
+}  // namespace gemm_epi
+
+template <int EPI, bool kLnFold, class Release>
+__device__ __forceinline__ void epilogue_boxes(uint32_t t_row, int col0, int row0, int M, int box_begin, int box_count,
+                                               const float* __restrict__ bias, const float* __restrict__ colsum,
+                                               float ln_mu, float ln_rstd, uint8_t* obuf, int& buf,
+                                               const CUtensorMap* tmC, Release&& release) {
+  using namespace gemm_epi;
+  constexpr bool kOutF32 = (EPI == DFD_EPI_STORE_F32 || EPI == DFD_EPI_ADD_F32);
+  constexpr int COLS_PER_BOX = kOutF32 ? 32 : 64;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int box = box_begin; box < box_begin + box_count; ++box) {
+    const int c = col0 + box * COLS_PER_BOX;
+    uint32_t packed[32];  // 128 bytes of output for this thread's row
+    if constexpr (kOutF32) {
+      uint32_t r[32];
+      tmem_ld32(t_row + box * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c + j)) : make_float4(0, 0, 0, 0);
+        packed[j + 0] = __float_as_uint(__uint_as_float(r[j + 0]) + b4.x);
+        packed[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
+        packed[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
+        packed[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
+      }
+    } else {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(t_row + box * 64 + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 b4 =
+              bias ? __ldg(reinterpret_cast<const float4*>(bias + c + half * 32 + j)) : make_float4(0, 0, 0, 0);
+          float v0, v1, v2, v3;
+          if constexpr (kLnFold) {
+            // LayerNorm folded into this GEMM: out = rstd * (acc - mu * colsum[n]) + bias'[n]
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(colsum + c + half * 32 + j));
+            v0 = fmaf(ln_rstd, fmaf(-ln_mu, c4.x, __uint_as_float(r[j + 0])), b4.x);
+            v1 = fmaf(ln_rstd, fmaf(-ln_mu, c4.y, __uint_as_float(r[j + 1])), b4.y);
+            v2 = fmaf(ln_rstd, fmaf(-ln_mu, c4.z, __uint_as_float(r[j + 2])), b4.z);
+            v3 = fmaf(ln_rstd, fmaf(-ln_mu, c4.w, __uint_as_float(r[j + 3])), b4.w);
+          } else {
+            v0 = __uint_as_float(r[j + 0]) + b4.x;
+            v1 = __uint_as_float(r[j + 1]) + b4.y;
+            v2 = __uint_as_float(r[j + 2]) + b4.z;
+            v3 = __uint_as_float(r[j + 3]) + b4.w;
+          }
+          if constexpr (EPI == DFD_EPI_STORE_BF16_QGELU || EPI == DFD_EPI_STORE_BF16_QGELU_LNFOLD) {
+            v0 = quick_gelu_fast(v0);
+            v1 = quick_gelu_fast(v1);
+            v2 = quick_gelu_fast(v2);
+            v3 = quick_gelu_fast(v3);
+          } else if constexpr (EPI == DFD_EPI_STORE_BF16_GELU) {
+            v0 = gelu_erf(v0);
+            v1 = gelu_erf(v1);
+            v2 = gelu_erf(v2);
+            v3 = gelu_erf(v3);
+          }
+          packed[half * 16 + j / 2 + 0] = pack_bf16(v0, v1);
+          packed[half * 16 + j / 2 + 1] = pack_bf16(v2, v3);
+        }
+      }
+    }
+    if (box == box_begin + box_count - 1) release();  // all TMEM reads of this accumulator are done in this warp
+    // staging buffer `buf` was last read by the TMA store issued two boxes ago
+    if (lane == 0) tma_store_wait_read<OUT_BUFS_PER_WARP - 1>();
+    __syncwarp();
+    uint8_t* dst = obuf + buf * OUT_BUF + lane * 128;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      // 128-byte swizzle: 16-byte chunk index XOR (row & 7); box base is 1024-byte aligned
+      uint4 v = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
+      *reinterpret_cast<uint4*>(dst + ((ch ^ (lane & 7)) << 4)) = v;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && row0 < M) {
+      if constexpr (EPI == DFD_EPI_ADD_F32 || EPI == DFD_EPI_ADD_BF16)
+        tma_reduce_add_2d(tmC, obuf + buf * OUT_BUF, c, row0);
+      else
+        tma_store_2d(tmC, obuf + buf * OUT_BUF, c, row0);
+    }
+    if (lane == 0) tma_store_commit();
+    buf ^= 1;
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -139,90 +238,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 2;
     uint8_t* obuf = smem + OFF_OUT + ew * (OUT_BUFS_PER_WARP * OUT_BUF);
     constexpr bool kOutF32 = (EPI == DFD_EPI_STORE_F32 || EPI == DFD_EPI_ADD_F32);
-    constexpr int COLS_PER_BOX = kOutF32 ? 32 : 64;
-    constexpr int NUM_BOX = BN / COLS_PER_BOX;
+    constexpr int NUM_BOX = BN / (kOutF32 ? 32 : 64);
+    static_assert(OUT_BUF == gemm_epi::OUT_BUF && OUT_BUFS_PER_WARP == gemm_epi::OUT_BUFS_PER_WARP, "epilogue staging");
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row0 = m_blk * BM + q * 32;
-      const int col0 = n_blk * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int box = 0; box < NUM_BOX; ++box) {
-        const int c = col0 + box * COLS_PER_BOX;
-        uint32_t packed[32];  // 128 bytes of output for this thread's row
-        if constexpr (kOutF32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + box * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c + j)) : make_float4(0, 0, 0, 0);
-            packed[j + 0] = __float_as_uint(__uint_as_float(r[j + 0]) + b4.x);
-            packed[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
-            packed[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
-            packed[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
-          }
-        } else {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld32(t_row + box * 64 + half * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 =
-                  bias ? __ldg(reinterpret_cast<const float4*>(bias + c + half * 32 + j)) : make_float4(0, 0, 0, 0);
-              float v0 = __uint_as_float(r[j + 0]) + b4.x;
-              float v1 = __uint_as_float(r[j + 1]) + b4.y;
-              float v2 = __uint_as_float(r[j + 2]) + b4.z;
-              float v3 = __uint_as_float(r[j + 3]) + b4.w;
-              if constexpr (EPI == DFD_EPI_STORE_BF16_QGELU) {
-                v0 = quick_gelu_fast(v0);
-                v1 = quick_gelu_fast(v1);
-                v2 = quick_gelu_fast(v2);
-                v3 = quick_gelu_fast(v3);
-              } else if constexpr (EPI == DFD_EPI_STORE_BF16_GELU) {
-                v0 = gelu_erf(v0);
-                v1 = gelu_erf(v1);
-                v2 = gelu_erf(v2);
-                v3 = gelu_erf(v3);
-              }
-              packed[half * 16 + j / 2 + 0] = pack_bf16(v0, v1);
-              packed[half * 16 + j / 2 + 1] = pack_bf16(v2, v3);
-            }
-          }
-        }
-        if (box == NUM_BOX - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
-        }
-        // staging buffer `buf` was last read by the TMA store issued two boxes ago
-        if (lane == 0) tma_store_wait_read<OUT_BUFS_PER_WARP - 1>();
-        __syncwarp();
-        uint8_t* dst = obuf + buf * OUT_BUF + lane * 128;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          // 128-byte swizzle: 16-byte chunk index XOR (row & 7); box base is 1024-byte aligned
-          uint4 v = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-          *reinterpret_cast<uint4*>(dst + ((ch ^ (lane & 7)) << 4)) = v;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && row0 < M) {
-          if constexpr (EPI == DFD_EPI_ADD_F32 || EPI == DFD_EPI_ADD_BF16)
-            tma_reduce_add_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
-          else
-            tma_store_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
-        }
-        if (lane == 0) tma_store_commit();
-        buf ^= 1;
-      }
+      epilogue_boxes<EPI, false>(t_row, n_blk * BN, row0, M, 0, NUM_BOX, bias, nullptr, 0.f, 0.f, obuf, buf, &tmC, [&]() {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);  // hand the accumulator back to the MMA warp (128 arrivals)
+      });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -567,9 +597,9 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) tma_store_wait_all<0>();
     } else {
     constexpr bool kOutF32 = (EPI == DFD_EPI_STORE_F32 || EPI == DFD_EPI_ADD_F32);
-    constexpr int COLS_PER_BOX = kOutF32 ? 32 : 64;
-    constexpr int NUM_BOX = BN / COLS_PER_BOX;
+    constexpr int NUM_BOX = BN / (kOutF32 ? 32 : 64);
     constexpr int BOX_PER_WARP = NUM_BOX / 2;
+    static_assert(OUT_BUF == gemm_epi::OUT_BUF && OUT_BUFS_PER_WARP == gemm_epi::OUT_BUFS_PER_WARP, "epilogue staging");
     const int box_begin = (ew >> 2) * BOX_PER_WARP;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -611,86 +641,13 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int box = box_begin; box < box_begin + BOX_PER_WARP; ++box) {
-        const int c = col0 + box * COLS_PER_BOX;
-        uint32_t packed[32];
-        if constexpr (kOutF32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + box * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c + j)) : make_float4(0, 0, 0, 0);
-            packed[j + 0] = __float_as_uint(__uint_as_float(r[j + 0]) + b4.x);
-            packed[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
-            packed[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
-            packed[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
-          }
-        } else {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld32(t_row + box * 64 + half * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 =
-                  bias ? __ldg(reinterpret_cast<const float4*>(bias + c + half * 32 + j)) : make_float4(0, 0, 0, 0);
-              float v0, v1, v2, v3;
-              if constexpr (kLnFold) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(ln.colsum + c + half * 32 + j));
-                v0 = fmaf(ln_rstd, fmaf(-ln_mu, c4.x, __uint_as_float(r[j + 0])), b4.x);
-                v1 = fmaf(ln_rstd, fmaf(-ln_mu, c4.y, __uint_as_float(r[j + 1])), b4.y);
-                v2 = fmaf(ln_rstd, fmaf(-ln_mu, c4.z, __uint_as_float(r[j + 2])), b4.z);
-                v3 = fmaf(ln_rstd, fmaf(-ln_mu, c4.w, __uint_as_float(r[j + 3])), b4.w);
-              } else {
-                v0 = __uint_as_float(r[j + 0]) + b4.x;
-                v1 = __uint_as_float(r[j + 1]) + b4.y;
-                v2 = __uint_as_float(r[j + 2]) + b4.z;
-                v3 = __uint_as_float(r[j + 3]) + b4.w;
-              }
-              if constexpr (EPI == DFD_EPI_STORE_BF16_QGELU || EPI == DFD_EPI_STORE_BF16_QGELU_LNFOLD) {
-                v0 = quick_gelu_fast(v0);
-                v1 = quick_gelu_fast(v1);
-                v2 = quick_gelu_fast(v2);
-                v3 = quick_gelu_fast(v3);
-              } else if constexpr (EPI == DFD_EPI_STORE_BF16_GELU) {
-                v0 = gelu_erf(v0);
-                v1 = gelu_erf(v1);
-                v2 = gelu_erf(v2);
-                v3 = gelu_erf(v3);
-              }
-              packed[half * 16 + j / 2 + 0] = pack_bf16(v0, v1);
-              packed[half * 16 + j / 2 + 1] = pack_bf16(v2, v3);
-            }
-          }
-        }
-        if (box == box_begin + BOX_PER_WARP - 1) {
-          // all TMEM reads of this accumulator are done in this warp: tell the leader's MMA thread
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
-        }
-        if (lane == 0) tma_store_wait_read<OUT_BUFS_PER_WARP - 1>();
-        __syncwarp();
-        uint8_t* dst = obuf + buf * OUT_BUF + lane * 128;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          uint4 v = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-          *reinterpret_cast<uint4*>(dst + ((ch ^ (lane & 7)) << 4)) = v;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && row0 < M) {
-          if constexpr (EPI == DFD_EPI_ADD_F32 || EPI == DFD_EPI_ADD_BF16)
-            tma_reduce_add_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
-          else
-            tma_store_2d(&tmC, obuf + buf * OUT_BUF, c, row0);
-        }
-        if (lane == 0) tma_store_commit();
-        buf ^= 1;
-      }
+      epilogue_boxes<EPI, kLnFold>(t_row, col0, row0, M, box_begin, BOX_PER_WARP, bias, ln.colsum, ln_mu, ln_rstd, obuf,
+                                   buf, &tmC, [&]() {
+                                     // tell the leader's MMA thread (one elected arrival per epilogue warp)
+                                     tc_fence_before();
+                                     __syncwarp();
+                                     if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+                                   });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -710,7 +667,7 @@ template <int EPI>
 static int launch(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                   const float* bias, int M, int N, int K, cudaStream_t stream) {
   using namespace gemm;
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64] = {};  // per device; a repeated cudaFuncSetAttribute is harmless
   if (!configured[ctx->device & 63]) {
     DFD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured[ctx->device & 63] = true;
@@ -728,7 +685,7 @@ static int launch2(const dfd_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap
                    const GemmLnArgs& ln = GemmLnArgs()) {
   using namespace gemm2;
   constexpr int SMEM = Cfg<EPI>::SMEM_BYTES;
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64] = {};  // per device; a repeated cudaFuncSetAttribute is harmless
   if (!configured[ctx->device & 63]) {
     DFD_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_2sm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured[ctx->device & 63] = true;

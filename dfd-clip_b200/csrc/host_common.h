@@ -11,6 +11,9 @@
 
 #include "../../include/dfdclip_b200.h"
 
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 // Optional per-kernel timing (dfd_timing_*): CUDA event pairs recorded on the launching stream around each
@@ -36,6 +39,28 @@ struct dfd_timing_slot {
   cudaEvent_t start, stop;
 };
 
+// Key of one encoded TMA descriptor: a descriptor depends only on these values, so repeated launches on the same
+// buffers (the steady state of a predict / training loop: the caching allocator hands back the same blocks) reuse it
+// instead of paying cuTensorMapEncodeTiled ~150 times per predict.
+struct dfd_tmap_key {
+  const void* base;
+  uint64_t d0, d1, d2, ld, ld2;
+  uint32_t box0, box1, misc;  // misc = dtype | elem_bytes << 8 | rank << 16 | swizzle << 24
+  bool operator==(const dfd_tmap_key& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && ld2 == o.ld2 && box0 == o.box0 &&
+           box1 == o.box1 && misc == o.misc;
+  }
+};
+struct dfd_tmap_key_hash {
+  size_t operator()(const dfd_tmap_key& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {k.d0, k.d1, k.d2, k.ld, k.ld2, static_cast<uint64_t>(k.box0) << 32 | k.box1,
+                       static_cast<uint64_t>(k.misc)})
+      h = (h ^ v) * 0x100000001B3ull + (h >> 29);
+    return static_cast<size_t>(h);
+  }
+};
+
 struct dfd_ctx {
   int device;
   int num_sms;
@@ -49,6 +74,10 @@ struct dfd_ctx {
   mutable cudaStream_t side_stream = nullptr;
   mutable cudaEvent_t fork_event = nullptr, join_event = nullptr;
   mutable std::vector<cudaEvent_t> tap_events;
+  // encoded TMA descriptors (see dfd_tmap_key); guarded by tmap_mutex, cleared when it reaches tmap_cache_max entries
+  mutable std::unordered_map<dfd_tmap_key, CUtensorMap, dfd_tmap_key_hash> tmap_cache;
+  mutable std::mutex tmap_mutex;
+  static constexpr size_t tmap_cache_max = 8192;
 };
 
 namespace dfd {

@@ -200,9 +200,14 @@ class _DecoderChainFn(torch.autograd.Function):
                 _native.ctx(dev), d, h, nb, ctypes.byref(plan["w"]), ctypes.byref(plan["taps"]),
                 _native.ptr(plan["mask"]), b, t, p, _native.ptr(plan["block_out"]), _native.ptr(saved), nbytes,
                 _native.stream_ptr(dev)))
+        # keep what the backward needs, but NOT the output tensor: ctx -> block_out -> grad_fn -> ctx would be a
+        # reference cycle that keeps the whole graph (and the parameters' AccumulateGrad nodes, with the stream they
+        # were created on) alive until the garbage collector runs
+        block_out = plan.pop("block_out")
+        plan.pop("video_feature", None)
         ctx.decoder, ctx.plan, ctx.saved_buf, ctx.nbytes = decoder, plan, saved, nbytes
         ctx.params = params
-        return plan["block_out"]
+        return block_out
 
     @staticmethod
     def backward(ctx, d_block_out):

@@ -75,11 +75,16 @@ class TrainStep:
         # the end); the tail / loss / SGD are ~30 torch kernels more
         self.launches_per_step = (4 + 7 * max(taps) + 2) + (1 + 12 * nb) + (19 * nb + 2 * (nb - 1) + 3)
         self.graph = None
+        # warm-up and capture run on ONE side stream: autograd runs a parameter's gradient accumulation on the stream
+        # that was current when its accumulator node was created, which must be the capturing stream
+        self._side = torch.cuda.Stream(dev)
         self._warm_up(max(1, int(warmup)))
         if graph:
+            import gc
+            gc.collect()  # no autograd graph of the warm-up may survive into the capture
             self.graph = torch.cuda.CUDAGraph()
             # thread_local: other threads (NVML sampling, NCCL's watchdog) may touch CUDA while this one captures
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            with torch.cuda.graph(self.graph, stream=self._side, capture_error_mode="thread_local"):
                 self.loss, self.logits = self._body()
 
     # ------------------------------------------------------------------------------------------ set-up
@@ -109,7 +114,7 @@ class TrainStep:
         opt, det = self.opt, self.det
         saved = [p.detach().clone() for p in self.params]
         buffers = [(b, b.detach().clone()) for b in det.buffers()]   # e.g. BatchNorm statistics of a 768-bn adapter
-        side = torch.cuda.Stream(self.dev)
+        side = self._side
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
             for _ in range(n):

@@ -116,11 +116,12 @@ def test_c5_training_step_matches_the_reference(cuda_device):
     sd, x, m = fullsize_inputs("vitb16_c5", g)
     det = build_detector(g, sd, cuda_device).train()
     labels = torch.from_numpy(g["labels"]).to(cuda_device)
-    losses, logits, other = det(x.to(cuda_device), [labels], m.to(cuda_device), comp=["raw"] * x.shape[0],
-                                speed=torch.ones(x.shape[0], device=cuda_device), train=True, single_task=0)
-    assert other == {}
-    loss = losses[0].mean()
-    loss.backward()
+    with torch.enable_grad():
+        losses, logits, other = det(x.to(cuda_device), [labels], m.to(cuda_device), comp=["raw"] * x.shape[0],
+                                    speed=torch.ones(x.shape[0], device=cuda_device), train=True, single_task=0)
+        assert other == {}
+        loss = losses[0].mean()
+        loss.backward()
     torch.cuda.synchronize()
     check_logits("c5", logits[0].detach().cpu().numpy(), g)
     assert abs(loss.item() - float(g["loss"])) <= TOL_LOGIT_ABS

@@ -320,8 +320,9 @@ def test_linear_f32_backward(cuda_device, b, n, k, gelu, add):
     torch.cuda.synchronize()
     ref_dx = dy.double() @ w.double()
     if gelu:  # x here is quickgelu(pre) in the chain; the kernel only needs pre for the derivative
-        p = pre.double().requires_grad_(True)
-        (p * torch.sigmoid(1.702 * p)).backward(ref_dx)
+        with torch.enable_grad():
+            p = pre.double().requires_grad_(True)
+            (p * torch.sigmoid(1.702 * p)).backward(ref_dx)
         ref_dx = p.grad
     if add:
         ref_dx = ref_dx + extra.double()
