@@ -133,46 +133,69 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 
 // ------------------------------------------------------------------------------------------- linear backward
 // dX[b,k] = sum_n dY[b,n] W[n,k]: CTA = (128 columns k, one chunk of DX_NC output features n, 16 rows b); thread = one
-// column, 16 row accumulators; W is read once, coalesced along k; partials [chunk][B][K] are reduced in order.
-constexpr int DX_KT = 128, DX_NC = 64, DX_BT = 16;
+// column, 16 row accumulators; W is read once, coalesced along k, DX_NC independent loads per thread issued up front
+// (the kernel is a latency chain otherwise: a few hundred small CTAs, one dependent global load per feature); the dY
+// chunk sits transposed in shared memory so that one feature's 16 row values are four broadcast 16-byte loads.
+// Partials [chunk][B][K] are reduced in a fixed order by lin_dx_reduce_kernel.
+constexpr int DX_KT = 128, DX_NC = 16, DX_BT = 16;
 
 __global__ void __launch_bounds__(DX_KT)
 lin_dx_partial_kernel(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ part, int B, int N,
                       int K) {
-  __shared__ float sdy[DX_BT][DX_NC];
+  __shared__ __align__(16) float sdy[DX_NC][DX_BT];
   const int k = blockIdx.x * DX_KT + threadIdx.x;
   const int n0 = blockIdx.y * DX_NC, b0 = blockIdx.z * DX_BT;
   const int nn = min(DX_NC, N - n0);
   for (int i = threadIdx.x; i < DX_BT * DX_NC; i += DX_KT) {
-    const int r = i / DX_NC, c = i % DX_NC;
-    sdy[r][c] = (b0 + r < B && c < nn) ? dy[static_cast<int64_t>(b0 + r) * N + n0 + c] : 0.f;
+    const int c = i / DX_BT, r = i % DX_BT;
+    sdy[c][r] = (b0 + r < B && c < nn) ? dy[static_cast<int64_t>(b0 + r) * N + n0 + c] : 0.f;
+  }
+  float w[DX_NC];
+  if (k < K) {
+    const float* wp = W + static_cast<int64_t>(n0) * K + k;
+#pragma unroll
+    for (int c = 0; c < DX_NC; ++c) w[c] = (c < nn) ? __ldg(wp + static_cast<int64_t>(c) * K) : 0.f;
   }
   __syncthreads();
+  if (k >= K) return;
   float acc[DX_BT];
 #pragma unroll
   for (int r = 0; r < DX_BT; ++r) acc[r] = 0.f;
-  if (k < K) {
-    const float* wp = W + static_cast<int64_t>(n0) * K + k;
-#pragma unroll 4
-    for (int c = 0; c < nn; ++c) {
-      const float w = __ldg(wp + static_cast<int64_t>(c) * K);
 #pragma unroll
-      for (int r = 0; r < DX_BT; ++r) acc[r] = fmaf(sdy[r][c], w, acc[r]);
+  for (int c = 0; c < DX_NC; ++c) {
+#pragma unroll
+    for (int r4 = 0; r4 < DX_BT; r4 += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(&sdy[c][r4]);
+      acc[r4 + 0] = fmaf(d.x, w[c], acc[r4 + 0]);
+      acc[r4 + 1] = fmaf(d.y, w[c], acc[r4 + 1]);
+      acc[r4 + 2] = fmaf(d.z, w[c], acc[r4 + 2]);
+      acc[r4 + 3] = fmaf(d.w, w[c], acc[r4 + 3]);
     }
-    float* dst = part + static_cast<int64_t>(blockIdx.y) * B * K;
-#pragma unroll
-    for (int r = 0; r < DX_BT; ++r)
-      if (b0 + r < B) dst[static_cast<int64_t>(b0 + r) * K + k] = acc[r];
   }
+  float* dst = part + static_cast<int64_t>(blockIdx.y) * B * K;
+#pragma unroll
+  for (int r = 0; r < DX_BT; ++r)
+    if (b0 + r < B) dst[static_cast<int64_t>(b0 + r) * K + k] = acc[r];
 }
 
 // dx[i] = (sum_s part[s][i]) * quickgelu'(pre[i]) + add[i];   quickgelu(x) = x sigmoid(1.702 x)  (model.py:166-168)
-__global__ void lin_dx_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ pre,
-                                     const float* add, float* dx, int64_t total) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+// CTA = 32 consecutive elements x 8 groups of splits: thread (g, e) sums splits g, g + 8, ... of element e (coalesced
+// 128-byte rows, independent loads), the 8 group sums are added in a fixed order through shared memory.
+__global__ void __launch_bounds__(256)
+lin_dx_reduce_kernel(const float* __restrict__ part, int splits, const float* __restrict__ pre, const float* add,
+                     float* dx, int64_t total) {
+  __shared__ float red[8][32];
+  const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + e;
   float v = 0.f;
-  for (int s = 0; s < splits; ++s) v += part[s * total + i];
+  if (i < total)
+    for (int s = g; s < splits; s += 8) v += part[s * total + i];
+  red[g][e] = v;
+  __syncthreads();
+  if (g != 0 || i >= total) return;
+  v = red[0][e];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) v += red[j][e];
   if (pre) {
     const float z = pre[i];
     const float sg = 1.f / (1.f + __expf(-1.702f * z));
@@ -252,8 +275,8 @@ int linear_f32_backward(const dfd_ctx* ctx, const float* x, const float* W, cons
     lin_dx_partial_kernel<<<grid, DX_KT, 0, stream>>>(dy, W, part, B, N, K);
     DFD_CUDA_OK(cudaGetLastError());
     const int64_t total = static_cast<int64_t>(B) * K;
-    lin_dx_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(part, splits, gelu_pre, dx_add,
-                                                                                         dx, total);
+    lin_dx_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 256, 0, stream>>>(part, splits, gelu_pre, dx_add, dx,
+                                                                                       total);
     DFD_CUDA_OK(cudaGetLastError());
   }
   if (dW) {

@@ -186,6 +186,39 @@ class TrainStep:
             self.graph.replay()
         return self.loss, self.logits
 
+    def run_host(self, batches):
+        """The trainer loop over HOST batches (the reference's DataLoader hands out CPU tensors that the Accelerate-
+        prepared loader copies to the device per step): ``batches`` yields ``(x, y, m)`` host tensors (pinned for real
+        overlap); the H2D copy of batch k+1 runs on a copy stream while step k computes. Yields ``(loss, logits)`` per
+        batch, views of the step's static buffers."""
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        copy = self._copy_stream
+
+        def issue(batch):
+            with torch.cuda.stream(copy):
+                bufs = [t.to(self.dev, non_blocking=True) for t in batch]
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return bufs, ev
+
+        it = iter(batches)
+        try:
+            nxt = issue(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = issue(next(it))   # in flight while this step runs
+            except StopIteration:
+                nxt = None
+            main.wait_event(cur[1])
+            for t in cur[0]:
+                t.record_stream(main)   # allocated on the copy stream, consumed on this one
+            yield self(*cur[0])
+
     def eager(self, x, y, m, speed=None):
         """The same step without the graph (per-kernel timing, debugging)."""
         self._load(x, y, m, speed)

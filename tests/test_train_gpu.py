@@ -477,3 +477,26 @@ def test_captured_graphs_survive_a_larger_eager_call(cuda_device):
         torch.cuda.synchronize()
         assert torch.equal(out, ref)
         del junk
+
+
+def test_train_step_run_host_matches_device_batches(cuda_device):
+    """TrainStep.run_host (H2D of the next batch overlapped with the current step) trains exactly like feeding the same
+    batches from the device."""
+    import copy
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.training import TrainStep
+    det_a, _ = _build_small_detector(cuda_device)
+    det_b = copy.deepcopy(det_a)
+    host = []
+    for i in range(4):
+        x, m = synthetic.make_clips(4, 3, 64, seed=90 + i)
+        y = torch.randint(0, 2, (4,), generator=torch.Generator().manual_seed(95 + i))
+        host.append((x.pin_memory(), y.pin_memory(), m.pin_memory()))
+    dev0 = tuple(t.to(cuda_device) for t in host[0])
+    step_a = TrainStep(det_a, det_a.configure_optimizers(lr=0.02), *dev0)
+    step_b = TrainStep(det_b, det_b.configure_optimizers(lr=0.02), *dev0)
+    losses_a = [step_a(*(t.to(cuda_device) for t in b))[0].item() for b in host]
+    losses_b = [loss.item() for loss, _ in step_b.run_host(iter(host))]
+    assert losses_a == losses_b
+    for p, q in zip(det_a.parameters(), det_b.parameters()):
+        assert torch.equal(p, q)
