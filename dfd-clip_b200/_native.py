@@ -164,7 +164,7 @@ def load_library():
         lib.dfd_decoder_train_backward.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
                                                    ctypes.POINTER(DecoderWeights), ctypes.POINTER(KvTaps), c_void_p,
                                                    c_int, c_int, c_int, c_void_p, _PP, _PP, c_void_p, c_size_t,
-                                                   c_void_p]
+                                                   c_int, c_int, c_void_p]
         lib.dfd_linear_f32_backward_workspace_bytes.argtypes = [c_int, c_int, c_int]
         lib.dfd_linear_f32_backward_workspace_bytes.restype = c_size_t
         lib.dfd_linear_f32_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

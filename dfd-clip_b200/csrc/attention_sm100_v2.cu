@@ -1,22 +1,29 @@
 // tcgen05 encoder self-attention, pipelined two-tile kernel for 128 < L <= 208 tokens per frame (CLIP ViT-B/16:
 // L = 197). Reference: MultiheadAttention.forward, src/clip/model.py:188-195 — softmax_k((q/8).k) v, no mask.
 //
-// Work item = (frame, head); one persistent CTA per SM, 320 threads:
+// Work item = (frame, head); one persistent CTA per SM, 352 threads:
 //   warp 0        TMA producer: Q [256 x 64] (rows >= L zero-filled), K [208 x 64], V [208 x 64] of the item into a
 //                 2-stage smem ring, so the loads of item i+1 overlap all compute of item i.
-//   warp 1        MMA issuer (one thread). Per 128-row query tile X in {A, B}:
+//   warp 1 / 10   MMA issuer of query tile A / B (128 rows each). The whole warp walks the loop with uniform control
+//                 flow and ONE elected lane issues, so TMEM addresses and smem descriptors stay in uniform registers
+//                 (under `if (lane == 0)` every tcgen05.mma paid an ELECT / 4 x R2UR / retry-branch sequence of ~95
+//                 cycles: the 13 P.V MMAs of ~32 tensor-core cycles each took 1 250 cycles on the critical chain).
 //                   S_X = Q_X K^T        tcgen05.mma M=128 N=208 K=16 x4, operands in smem, fp32 S in TMEM
 //                   O_X = P_X V          tcgen05.mma M=128 N=64  K=16 x13, A = P from TMEM (bf16 pairs written by the
 //                                        softmax warps over the dead S columns), B = V from smem (MN-major)
-//                 issue order PV_A(i), S_A(i+1), PV_B(i), S_B(i+1): the tensor core works for one tile while the
-//                 other tile's warpgroup is in its softmax. The MUFU-bound exp2 pass is ping-ponged between the two
-//                 warpgroups with named barriers, so the tiles settle half a period apart instead of halving each
-//                 other's MUFU rate (measured: 164 -> 158 us per layer at 512 frames x 12 heads).
+//                 Per tile: PV(i) as soon as its P is complete, S(i+1) as soon as its O is drained; the two tiles'
+//                 chains only meet at the smem stage release (both commit to stage_empty).
 //   warps 2..5    softmax + epilogue warpgroup of tile A (thread = query row), warps 6..9 the same for tile B:
 //                 pass 1 row max out of TMEM, pass 2 exp2 / row sum / bf16 P back into TMEM (tcgen05.st), then
 //                 O: tcgen05.ld, 1/rowsum, bf16, swizzled smem staging, TMA store (rows >= L clipped by the map).
+//                 The MUFU-bound pass 2 is ping-ponged between the two warpgroups with named barriers, so the tiles
+//                 settle half a period apart. For L = 197 (compile-time instance) pass 2 runs in 16-key steps with
+//                 the next step's arguments and the previous step's sums / packing interleaved with the MUFU stream
+//                 (softmax_pass2_scheduled).
 // TMEM (512 columns): tile X owns columns [256 X, 256 X + 208): S fp32 [0,208); P bf16x2 [0,104) once S is consumed;
 // O fp32 [128,192) (S columns that pass 2 has already read).
+// Round-2 timeline at C2 (clock64, profiles/r2_mha_timeline.md): per tile max 500 + exp2 2 430 + P.V 650 + drain 700 +
+// next S 300-800 cycles; 152 -> 132 us per launch (512 frames x 12 heads).
 #include "common.cuh"
 #include "host_common.h"
 #include <stdlib.h>
@@ -34,7 +41,7 @@ namespace attn2 {
 constexpr int QT = 128;
 constexpr int KP = 208;
 constexpr int DH = 64;
-constexpr int THREADS = 320;
+constexpr int THREADS = 352;  // producer, MMA issuer of tile A, 2 x 4 softmax warps, MMA issuer of tile B
 constexpr int Q_BYTES = 2 * QT * 128;   // 32 KB
 constexpr int KV_BYTES = KP * 128;      // 26 KB
 constexpr int STAGE_BYTES = Q_BYTES + 2 * KV_BYTES;
@@ -120,10 +127,65 @@ __device__ __forceinline__ void exp2_chunk(float (&e)[32], const uint32_t (&cur)
   }
 }
 
+// Softmax pass 2 with a compile-time sequence length, in steps of 16 keys, software-pipelined so that every MUFU.EX2
+// has independent FMA-pipe work next to it. Why: with one softmax warp per sub-partition the pass is a single in-order
+// instruction stream; MUFU.EX2 issues 4 lanes per clock (8 cycles per warp instruction), and in the chunked version
+// above ptxas clusters 24-32 MUFUs back to back (nothing else is ready: the next chunk's arguments wait on its TMEM
+// load, the sums wait on the MUFU results), then runs the FFMA / FADD / F2FP bursts with the MUFU pipe idle — ncu
+// source view (profiles/r2_mha_sass_schedule.md): ~14 cycles per element against the pipe's 8. Here step k issues, per
+// key j:   e_k[j] = ex2(arg_k[j])   |   arg_{k+1}[j] = s_{k+1}[j] * sc - max   |   sum += e_{k-1}[j], pack e_{k-1}
+// — three independent streams (S of step k+1 was loaded during step k-1), so the scheduler can put ~3 FMA-pipe
+// instructions into each MUFU's 8-cycle shadow. Keys >= LCT are compile-time zeros (no MUFU, no select).
+template <int LCT>
+__device__ __forceinline__ float softmax_pass2_scheduled(uint32_t t_row, float sc, float mo) {
+  constexpr int NSTEP = 13;  // 208 / 16
+  uint32_t sa[16], sb[16];   // raw S of steps k+1 / k+2 (alternating)
+  float arga[16], argb[16];  // exp2 arguments of steps k / k+1
+  float ea[16], eb[16];      // exp2 results of steps k / k-1
+  float sum0 = 0.f, sum1 = 0.f;
+  // prologue: S of step 0 -> arguments of step 0; S of step 1 in flight
+  tmem_ld16(t_row, sa);
+  tmem_ld_wait();
+  tmem_ld16(t_row + 16, sb);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) arga[j] = fmaf(__uint_as_float(sa[j]), sc, -mo);
+#pragma unroll
+  for (int k = 0; k <= NSTEP; ++k) {
+    // S of step k+1 has landed (issued one step ago); start the load of step k+2 into the other buffer
+    uint32_t (&s_next)[16] = (k & 1) ? sa : sb;    // step k+1
+    uint32_t (&s_after)[16] = (k & 1) ? sb : sa;   // step k+2
+    float (&arg_cur)[16] = (k & 1) ? argb : arga;
+    float (&arg_next)[16] = (k & 1) ? arga : argb;
+    float (&e_cur)[16] = (k & 1) ? eb : ea;
+    float (&e_prev)[16] = (k & 1) ? ea : eb;
+    if (k + 1 < NSTEP) tmem_ld_wait();
+    if (k + 2 < NSTEP) tmem_ld16(t_row + (k + 2) * 16, s_after);
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (k < NSTEP) e_cur[j] = (k * 16 + j < LCT) ? fast_exp2(arg_cur[j]) : 0.f;
+      if (k + 1 < NSTEP && (k + 1) * 16 + j < LCT) arg_next[j] = fmaf(__uint_as_float(s_next[j]), sc, -mo);
+      if (k > 0) {
+        if (j & 1) {
+          sum1 += e_prev[j];
+          pk[j >> 1] = pack_bf16(e_prev[j - 1], e_prev[j]);
+        } else {
+          sum0 += e_prev[j];
+        }
+      }
+    }
+    if (k > 0) tmem_st8(t_row + (k - 1) * 8, pk);
+  }
+  tmem_st_wait();
+  return sum0 + sum1;
+}
+
+template <int LCT>
 __global__ void __launch_bounds__(attn2::THREADS, 1)
 mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                   const __grid_constant__ CUtensorMap tmO, int L, int H, int num_items) {
+                   const __grid_constant__ CUtensorMap tmO, int L_rt, int H, int num_items) {
   using namespace attn2;
+  const int L = LCT > 0 ? LCT : L_rt;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
@@ -134,7 +196,9 @@ mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* o_full = bars + 8;
   uint64_t* o_empty = bars + 10;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + TMEM_PTR_OFF);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform by construction: tell the compiler so (values that pass through shfl from lane 0 are treated as
+  // uniform, which keeps everything derived from them — TMEM addresses, smem descriptors — in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int D = H * DH;
   const int n_my = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
@@ -147,7 +211,7 @@ mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&load_full[i], 1);
-        mbar_init(&stage_empty[i], 1);
+        mbar_init(&stage_empty[i], 2);  // both tiles' MMA issuers commit their last read of the stage
         mbar_init(&s_full[i], 1);
         mbar_init(&p_full[i], 128);
         mbar_init(&o_full[i], 1);
@@ -162,7 +226,7 @@ mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ TMA producer
@@ -179,69 +243,70 @@ mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_3d(&tmKV, &load_full[st], sb + V_OFF, 2 * D + h * DH, 0, f, kEvictFirst);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && n_my > 0) {
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------------------------------------ MMA issuers
+    // One issuing thread PER TILE (warp 1: tile A, warp 10: tile B). With a single thread serving both tiles in a
+    // fixed order, a tile whose P was ready had to wait until the thread had finished waiting for the OTHER tile's
+    // epilogue (clock64 timeline, profiles/r2_mha_timeline.md: P written -> O ready 1 150 - 1 450 cycles for 13 MMAs
+    // of ~35 cycles): head-of-line blocking on the critical chain S -> max -> exp -> PV -> drain of each tile.
+    // The whole warp walks the loop (uniform control flow, every lane polls the barriers) and ONE elected lane
+    // executes the tcgen05 instructions: with the loop under `if (lane == 0)` every operand lived in a vector register
+    // and each MMA cost an ELECT / 4 x R2UR / retry-branch sequence (~95 cycles per issue in the clock64 timeline:
+    // the 13 P.V MMAs of ~32 tensor-core cycles each took 1 250 cycles).
+    const int x = warp == 1 ? 0 : 1;
+    if (n_my > 0) {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KP);
       constexpr uint32_t idesc_o = umma_idesc_bf16(QT, DH, /*b_mn_major=*/true);
-      auto issue_s = [&](int x, int st) {
+      const uint32_t t_tile = tmem_base + x * TILE_COLS;
+      auto issue_s = [&](int st) {
         const uint8_t* sb = smem + st * STAGE_BYTES;
         const uint64_t q_desc = umma_desc_sw128(sb + Q_OFF + x * (QT * 128));
         const uint64_t k_desc = umma_desc_sw128(sb + K_OFF);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16(tmem_base + x * TILE_COLS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[x]);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(t_tile, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[x]);
+        }
+        __syncwarp();
       };
-      auto issue_pv = [&](int x, int st) {
+      auto issue_pv = [&](int st) {
         const uint8_t* sb = smem + st * STAGE_BYTES;
         const uint64_t v_desc = umma_desc_sw128_mn(sb + V_OFF);
-        const uint32_t t_tile = tmem_base + x * TILE_COLS;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < KP / 16; ++kk)
-          umma_bf16_ts(t_tile + O_COL, t_tile + kk * 8, v_desc + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_o,
-                       kk != 0);
-        umma_commit(&o_full[x]);
+          for (int kk = 0; kk < KP / 16; ++kk)
+            umma_bf16_ts(t_tile + O_COL, t_tile + kk * 8, v_desc + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_o,
+                         kk != 0);
+          umma_commit(&o_full[x]);
+          umma_commit(&stage_empty[st]);  // this tile's last read of the stage (the producer waits for both tiles)
+        }
+        __syncwarp();
       };
-      // Fixed issue order PV_A(i), S_A(i+1), PV_B(i), S_B(i+1). (A polling scheduler that served whichever tile was
-      // ready first measured slower: 195 vs 160 us per layer.)
       mbar_wait(&load_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
+      issue_s(0);
       for (int it = 0; it < n_my; ++it) {
         const int st = it & 1;
         const uint32_t ph = it & 1;
-        const bool nxt = it + 1 < n_my;
-        const int nst = (it + 1) & 1;
-        mbar_wait(&p_full[0], ph);
+        mbar_wait(&p_full[x], ph);
         tc_fence_after();
-        TRACE(0);
-        issue_pv(0, st);
-        if (nxt) {
+        if (x == 0) TRACE(0);
+        issue_pv(st);
+        if (it + 1 < n_my) {
+          const int nst = (it + 1) & 1;
           mbar_wait(&load_full[nst], ((it + 1) >> 1) & 1);
-          TRACE(1);
-          mbar_wait(&o_empty[0], ph);
+          if (x == 0) TRACE(1);
+          mbar_wait(&o_empty[x], ph);    // O (aliasing S columns) drained by this tile's epilogue
           tc_fence_after();
-          TRACE(2);
-          issue_s(0, nst);
-        }
-        mbar_wait(&p_full[1], ph);
-        tc_fence_after();
-        TRACE(3);
-        issue_pv(1, st);
-        umma_commit(&stage_empty[st]);
-        if (nxt) {
-          mbar_wait(&o_empty[1], ph);
-          tc_fence_after();
-          TRACE(4);
-          issue_s(1, nst);
+          if (x == 0) TRACE(2);
+          issue_s(nst);
         }
       }
     }
   } else {
     // ------------------------------------------------------------------------------ softmax + epilogue warps
-    const int x = (warp - 2) >> 2;         // query tile of this warpgroup
+    const int x = (warp - 2) >> 2;         // query tile of this warpgroup (warps 2..5: A, 6..9: B)
     const int q = warp & 3;                // TMEM lane quarter this warp may access
     const int row0 = x * QT + q * 32;      // first query row of this warp inside the frame
     const bool warp_active = row0 < L;
@@ -291,48 +356,52 @@ mha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (warp == 2) TRACE(6);
       if (warp == 6) TRACE(11);
       if (warp_active) {
-        uint32_t ra[32], rb[32];
-        // ---- pass 2: p = exp2(s*sc - max*sc), row sum, bf16 pairs back into TMEM columns [16c, 16c+16).
-        // Software pipelined: the exp2 of chunk c are issued (MUFU) before the sums / packing / tcgen05.st of
-        // chunk c-1, so the MUFU pipe always has independent work queued behind it.
-        float sum0 = 0.f, sum1 = 0.f;
-        float ea[32], eb[32];
-        ld_chunk(t_row, 0, ra);
-#pragma unroll
-        for (int c = 0; c <= NCHUNK; ++c) {
-          if (c < NCHUNK) {
-            uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-            uint32_t (&nx)[32] = (c & 1) ? ra : rb;
-            float (&e)[32] = (c & 1) ? eb : ea;
-            tmem_ld_wait();
-            if (c + 1 < NCHUNK) ld_chunk(t_row, c + 1, nx);
-            const int c0 = c * 32, w = (c < 6) ? 32 : 16;
-            if (c < 4 || c0 + w <= L) {
-              exp2_chunk<0>(e, cur, sc, mo, w);
-            } else {
-#pragma unroll
-              for (int j = 0; j < w; ++j)
-                e[j] = (c0 + j < L) ? fast_exp2(fmaf(__uint_as_float(cur[j]), sc, -mo)) : 0.f;
+        if constexpr (LCT > 0) {
+          inv_sum = 1.f / softmax_pass2_scheduled<LCT>(t_row, sc, mo);
+        } else {
+          uint32_t ra[32], rb[32];
+          // ---- pass 2: p = exp2(s*sc - max*sc), row sum, bf16 pairs back into TMEM columns [16c, 16c+16).
+          // Software pipelined: the exp2 of chunk c are issued (MUFU) before the sums / packing / tcgen05.st of
+          // chunk c-1, so the MUFU pipe always has independent work queued behind it.
+          float sum0 = 0.f, sum1 = 0.f;
+          float ea[32], eb[32];
+          ld_chunk(t_row, 0, ra);
+  #pragma unroll
+          for (int c = 0; c <= NCHUNK; ++c) {
+            if (c < NCHUNK) {
+              uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+              uint32_t (&nx)[32] = (c & 1) ? ra : rb;
+              float (&e)[32] = (c & 1) ? eb : ea;
+              tmem_ld_wait();
+              if (c + 1 < NCHUNK) ld_chunk(t_row, c + 1, nx);
+              const int c0 = c * 32, w = (c < 6) ? 32 : 16;
+              if (c < 4 || c0 + w <= L) {
+                exp2_chunk<0>(e, cur, sc, mo, w);
+              } else {
+  #pragma unroll
+                for (int j = 0; j < w; ++j)
+                  e[j] = (c0 + j < L) ? fast_exp2(fmaf(__uint_as_float(cur[j]), sc, -mo)) : 0.f;
+              }
+            }
+            if (c > 0) {
+              const int cp = c - 1, wp = (cp < 6) ? 32 : 16;
+              float (&e)[32] = (cp & 1) ? eb : ea;
+              uint32_t pk[16];
+  #pragma unroll
+              for (int j = 0; j < wp; j += 2) {
+                sum0 += e[j];
+                sum1 += e[j + 1];
+                pk[j >> 1] = pack_bf16(e[j], e[j + 1]);
+              }
+              if (cp < 6)
+                tmem_st16(t_row + cp * 16, pk);
+              else
+                tmem_st8(t_row + cp * 16, pk);
             }
           }
-          if (c > 0) {
-            const int cp = c - 1, wp = (cp < 6) ? 32 : 16;
-            float (&e)[32] = (cp & 1) ? eb : ea;
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < wp; j += 2) {
-              sum0 += e[j];
-              sum1 += e[j + 1];
-              pk[j >> 1] = pack_bf16(e[j], e[j + 1]);
-            }
-            if (cp < 6)
-              tmem_st16(t_row + cp * 16, pk);
-            else
-              tmem_st8(t_row + cp * 16, pk);
-          }
+          tmem_st_wait();
+          inv_sum = 1.f / (sum0 + sum1);
         }
-        tmem_st_wait();
-        inv_sum = 1.f / (sum0 + sum1);
       }
       // pass the MUFU turn to the other tile (tile B does not hand back after its last item)
       if (x == 0 || it + 1 < n_my) nbar_arrive(2 - x, 256);
@@ -405,12 +474,19 @@ int mha_fwd_tc2(const dfd_ctx* ctx, const void* qkv, void* mix, int n_frames, in
                        static_cast<uint64_t>(L) * D, 32, DH));
   static std::atomic<bool> configured[64] = {};  // per device; a repeated cudaFuncSetAttribute is harmless
   if (!configured[ctx->device & 63]) {
-    DFD_CUDA_OK(cudaFuncSetAttribute(mha_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DFD_CUDA_OK(cudaFuncSetAttribute(mha_fwd_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DFD_CUDA_OK(cudaFuncSetAttribute(mha_fwd_tc2_kernel<197>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured[ctx->device & 63] = true;
   }
   const int num_items = n_frames * H;
   const int grid = num_items < ctx->num_sms ? num_items : ctx->num_sms;
-  mha_fwd_tc2_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, L, H, num_items);
+  // L = 197 (every 224-pixel / patch-16 CLIP ViT): the instance with the sequence length at compile time and the
+  // scheduled softmax pass; DFD_MHA_GENERIC=1 keeps the run-time-L instance for A/B runs
+  static const bool generic = getenv("DFD_MHA_GENERIC") && atoi(getenv("DFD_MHA_GENERIC")) != 0;
+  if (L == 197 && !generic)
+    mha_fwd_tc2_kernel<197><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, L, H, num_items);
+  else
+    mha_fwd_tc2_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmKV, tmO, L, H, num_items);
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -396,13 +396,19 @@ int decoder_train_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const 
 
 // grads: same layout as dfd_decoder_weights, every pointer an OUTPUT (fp32, shapes of the parameters); ln_post_* are
 // not touched (the tail belongs to the caller). d_block_out: fp32 [B, n_blocks, D] gradient of every block output.
+// Blocks block_hi .. block_lo (descending) are processed by this call; a caller that wants to do something between
+// blocks (all-reduce a finished block's gradients while the next block's backward runs) walks from n_blocks - 1 down
+// to 0 in several calls: the gradient in flight lives in `saved`. positional_embedding's gradient is complete, and
+// class_embedding / ln_pre gradients are written, by the call that includes block 0.
 int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
                            const dfd_decoder_weights* grads, const dfd_kv_taps* taps, const uint8_t* mask, int B, int T,
                            int P, const float* d_block_out, float* const* dk, float* const* dv, void* saved,
-                           size_t saved_bytes, cudaStream_t stream) {
+                           size_t saved_bytes, int block_hi, int block_lo, cudaStream_t stream) {
   const TrainBuf tb = train_layout(B, T, D, H, n_blocks);
   DFD_TRY(check_train_args(D, H, n_blocks, w, taps, mask, B, T, P, saved, saved_bytes, tb));
   DFD_CHECK_ARG(grads && d_block_out, "decoder_train_backward: null pointer");
+  DFD_CHECK_ARG(0 <= block_lo && block_lo <= block_hi && block_hi < n_blocks,
+                "decoder_train_backward: block range [%d, %d] outside [0, %d)", block_lo, block_hi, n_blocks);
   uint8_t* base = static_cast<uint8_t*>(saved);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   auto G = [](const float* p) { return const_cast<float*>(p); };
@@ -410,9 +416,9 @@ int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const
   float *dx = F(tb.dx), *dx1 = F(tb.dx1), *dy = F(tb.dy), *dqs = F(tb.dqs), *dmix = F(tb.dmix), *dh = F(tb.dh);
   float* lin = F(tb.lin);
   const int cthr = 256, cblk = (D + cthr - 1) / cthr;
-  bool pe_written = false;
+  bool pe_written = block_hi != n_blocks - 1;  // an earlier call already wrote the last block's share
   // dx = gradient wrt the output of the last block
-  for (int i = n_blocks - 1; i >= 0; --i) {
+  for (int i = block_hi; i >= block_lo; --i) {
     const size_t bo = tb.blk_stride * i;
     float *x_in = F(bo + tb.x_in), *y1 = F(bo + tb.y1), *qs = F(bo + tb.qs), *mix = F(bo + tb.mix),
           *x1 = F(bo + tb.x1), *y2 = F(bo + tb.y2), *hpre = F(bo + tb.hpre), *h = F(bo + tb.h);
@@ -480,6 +486,7 @@ int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const
       DFD_CUDA_OK(cudaGetLastError());
     }
   }
+  if (block_lo > 0) return 0;
   // x0[b] = ln_pre(class_embedding) for every b: the B gradient rows collapse onto the one input row
   column_sum_kernel<<<cblk, cthr, 0, stream>>>(dx, dy, B, D, 0);                        // dy[0,:] = sum_b dx[b,:]
   ln_rows_bwd_param_kernel<<<cblk, cthr, 0, stream>>>(w->class_embedding, 0, F(tb.st_pre), dy,
@@ -511,11 +518,11 @@ int dfd_decoder_train_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const df
 int dfd_decoder_train_backward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
                                const dfd_decoder_weights* grads, const dfd_kv_taps* taps, const uint8_t* mask, int B,
                                int T, int P, const float* d_block_out, float* const* dk, float* const* dv, void* saved,
-                               size_t saved_bytes, void* stream) {
+                               size_t saved_bytes, int block_hi, int block_lo, void* stream) {
   dfd::clear_error();
   if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_decoder_train_backward: ctx is NULL");
   return dfd::decoder_train_backward(ctx, D, H, n_blocks, w, grads, taps, mask, B, T, P, d_block_out, dk, dv, saved,
-                                     saved_bytes, static_cast<cudaStream_t>(stream));
+                                     saved_bytes, block_hi, block_lo, static_cast<cudaStream_t>(stream));
 }
 
 int dfd_linear_f32_backward(dfd_ctx* ctx, const float* x, const float* W, const float* dy, const float* gelu_pre,

@@ -226,11 +226,18 @@ class _DecoderChainFn(torch.autograd.Function):
                 returned.append(None)  # written in place into the caller's gradient buffer
             grads.append(buf)
         gw, keep = decoder._weights_struct(grads)
+        # a block hook (training.TrainStep on several GPUs) is called after each block's gradients are complete, so
+        # that their all-reduce overlaps the backward of the blocks below
+        hook = getattr(decoder, "_block_grad_hook", None)
+        ranges = [(i, i) for i in range(nb - 1, -1, -1)] if hook is not None else [(nb - 1, 0)]
         with torch.cuda.device(dev):
-            _native.check(lib.dfd_decoder_train_backward(
-                _native.ctx(dev), d, h, nb, ctypes.byref(plan["w"]), ctypes.byref(gw), ctypes.byref(plan["taps"]),
-                _native.ptr(plan["mask"]), b, t, p, _native.ptr(d_block_out), None, None, _native.ptr(ctx.saved_buf),
-                ctx.nbytes, _native.stream_ptr(dev)))
+            for hi, lo in ranges:
+                _native.check(lib.dfd_decoder_train_backward(
+                    _native.ctx(dev), d, h, nb, ctypes.byref(plan["w"]), ctypes.byref(gw), ctypes.byref(plan["taps"]),
+                    _native.ptr(plan["mask"]), b, t, p, _native.ptr(d_block_out), None, None,
+                    _native.ptr(ctx.saved_buf), ctx.nbytes, hi, lo, _native.stream_ptr(dev)))
+                if hook is not None:
+                    hook(hi)
         del keep
         return (None, None, None) + tuple(returned)
 

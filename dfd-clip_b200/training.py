@@ -109,6 +109,47 @@ class TrainStep:
         chain = {id(p) for p in self.det.decoder._chain_params()}
         self.det.decoder._grad_sink = {id(p): p.grad for p in self.params if id(p) in chain}
         self._tail = [p for p in self.params if id(p) not in chain]
+        # Several GPUs: the gradients of decoder block i are complete as soon as the native backward has walked past
+        # it, so their all-reduce starts then (on a communication stream) and overlaps the backward of the blocks
+        # below; what is not inside a block's contiguous slice of the flat buffer is reduced after the backward.
+        self._block_slices, self._rest_slices = None, [(0, total)]
+        self.det.decoder._block_grad_hook = None
+        if self.world > 1:
+            span = {id(p): (o, (p.numel() + 3) // 4 * 4) for p, o in zip(self.params, offs)}
+            slices = []
+            for blk in self.det.decoder.transformer.resblocks:
+                ids = [id(p) for p in blk.parameters()]
+                if not ids or any(i not in span for i in ids):
+                    slices = None
+                    break
+                lo = min(span[i][0] for i in ids)
+                hi = max(span[i][0] + span[i][1] for i in ids)
+                if sum(span[i][1] for i in ids) != hi - lo:   # not contiguous in the optimizer's parameter order
+                    slices = None
+                    break
+                slices.append((lo, hi))
+            if slices and all(a[1] <= b[0] for a, b in zip(slices, slices[1:])):
+                self._block_slices = slices
+                rest, pos = [], 0
+                for lo, hi in slices:
+                    if lo > pos:
+                        rest.append((pos, lo))
+                    pos = hi
+                if pos < total:
+                    rest.append((pos, total))
+                self._rest_slices = rest
+                self._comm = torch.cuda.Stream(self.dev)
+                self.det.decoder._block_grad_hook = self._reduce_block
+
+    def _reduce_block(self, i):
+        """Called by the native decoder backward (on autograd's thread, forward stream current) once block i's
+        gradients are written: average them across the ranks on the communication stream."""
+        lo, hi = self._block_slices[i]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self._comm.wait_event(ev)
+        with torch.cuda.stream(self._comm):
+            self.dist.all_reduce(self.flat[lo:hi], op=self.dist.ReduceOp.AVG, group=self.group)
 
     def _warm_up(self, n):
         opt, det = self.opt, self.det
@@ -144,8 +185,17 @@ class TrainStep:
                 loss = loss + v
             loss.backward()
         if self.world > 1:
-            # DDP's gradient averaging as ONE collective on the flat buffer (NCCL over NVLink, captured in the graph)
-            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG, group=self.group)
+            # DDP's gradient averaging (NCCL over NVLink, captured in the graph): the decoder blocks' slices were
+            # started from inside the backward (_reduce_block); the rest of the flat buffer follows here
+            main = torch.cuda.current_stream(self.dev)
+            if self._block_slices is None:
+                self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG, group=self.group)
+            else:
+                self._comm.wait_stream(main)
+                with torch.cuda.stream(self._comm):
+                    for lo, hi in self._rest_slices:
+                        self.dist.all_reduce(self.flat[lo:hi], op=self.dist.ReduceOp.AVG, group=self.group)
+                main.wait_stream(self._comm)
         self.opt.step()
         return loss.detach(), logits[self.task].detach()
 
@@ -227,7 +277,9 @@ class TrainStep:
     def describe(self):
         return ("Detector.forward(train=True) + backward + %sfused SGD, %s; native encoder, native decoder chain "
                 "forward/backward (dfd_decoder_train_*), gradients in one flat fp32 buffer" % (
-                    "all_reduce(AVG) over %d ranks + " % self.world if self.world > 1 else "",
+                    "all_reduce(AVG) over %d ranks (%s) + " % (
+                        self.world, "per decoder block, overlapped with the backward" if self._block_slices
+                        else "one call") if self.world > 1 else "",
                     "one CUDA graph replay per step" if self.graph is not None else "eager"))
 
 

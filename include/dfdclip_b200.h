@@ -359,7 +359,10 @@ int dfd_resize_crop_u8(dfd_ctx* ctx, const uint8_t* frames, int n_frames, int H,
  * (class_embedding, positional_embedding [summed over the blocks], ln_pre_*, per block ln_1_*, in_proj_*, out_proj_*,
  * ln_2_*, c_fc_*, c_proj_*, augment_query; ln_post_* and attn_mode are ignored). dk / dv: NULL, or HOST arrays of
  * n_blocks device pointers to contiguous fp32 [B, T, P, H, 64] buffers for the gradients w.r.t. the tapped K / V (a
- * trainable adapter on the taps). op_mode.attn_mode != 0 is rejected. fp32 throughout, deterministic. */
+ * trainable adapter on the taps). Blocks block_hi .. block_lo (descending) are processed by one call: (n_blocks - 1, 0)
+ * does everything; a caller that overlaps a gradient all-reduce with the backward walks down in several calls (the
+ * gradient in flight lives in `saved`; class_embedding / ln_pre gradients come with the call that includes block 0,
+ * positional_embedding's is complete after it). op_mode.attn_mode != 0 is rejected. fp32 throughout, deterministic. */
 size_t dfd_decoder_train_bytes(int B, int T, int D, int n_blocks);
 int dfd_decoder_train_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
                               const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
@@ -367,7 +370,7 @@ int dfd_decoder_train_forward(dfd_ctx* ctx, int D, int H, int n_blocks, const df
 int dfd_decoder_train_backward(dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
                                const dfd_decoder_weights* grads, const dfd_kv_taps* taps, const uint8_t* mask, int B,
                                int T, int P, const float* d_block_out, float* const* dk, float* const* dv, void* saved,
-                               size_t saved_bytes, void* stream);
+                               size_t saved_bytes, int block_hi, int block_lo, void* stream);
 
 /* Backward of one of the decoder's nn.Linear layers (dfd_linear_f32), exported for unit tests:
  * dx[b,k] = (sum_n dy[b,n] W[n,k]) * quickgelu'(gelu_pre[b,k]) + dx_add[b,k];  dW[n,k] = sum_b dy[b,n] x[b,k];
