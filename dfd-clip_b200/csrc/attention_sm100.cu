@@ -49,7 +49,8 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* o_full = bars + 3;
   uint64_t* o_empty = bars + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + TMEM_PTR_OFF);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform values through a lane-0 shuffle: what derives from them stays in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int D = H * DH;
 
   if (warp == 0 && lane == 0) {
@@ -73,7 +74,7 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ TMA producer
@@ -91,7 +92,10 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // whole warp in the loop, ONE elected lane issues: the tcgen05 operands stay in uniform registers (see
+    // attention_sm100_v2.cu for the measurement behind this)
+    {
+      const bool elected = elect_one();
       constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KP);
       constexpr uint32_t idesc_o = umma_idesc_bf16(QT, DH, /*b_mn_major=*/true);
       uint32_t it = 0;
@@ -102,19 +106,25 @@ mha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_after();
         const uint64_t q_desc = umma_desc_sw128(smem + Q_OFF);
         const uint64_t k_desc = umma_desc_sw128(smem + K_OFF);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tmem_base, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+        }
+        __syncwarp();
         mbar_wait(p_full, ph);
         tc_fence_after();
         const uint64_t v_desc = umma_desc_sw128_mn(smem + V_OFF);
+        if (elected) {
 #pragma unroll
-        for (int kk = 0; kk < KP / 16; ++kk) {
-          // A: P chunk kk/4 (16 KB each), 32-byte step inside the swizzle atom; B: 16 keys = 2048 bytes of V rows
-          const uint64_t p_desc = umma_desc_sw128(smem + (kk >> 2) * (QT * 128)) + 2 * (kk & 3);
-          umma_bf16(tmem_base, p_desc, v_desc + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_o, kk != 0);
+          for (int kk = 0; kk < KP / 16; ++kk) {
+            // A: P chunk kk/4 (16 KB each), 32-byte step inside the swizzle atom; B: 16 keys = 2048 bytes of V rows
+            const uint64_t p_desc = umma_desc_sw128(smem + (kk >> 2) * (QT * 128)) + 2 * (kk & 3);
+            umma_bf16(tmem_base, p_desc, v_desc + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_o, kk != 0);
+          }
+          umma_commit(o_full);
         }
-        umma_commit(o_full);
+        __syncwarp();
       }
     }
   } else {

@@ -133,7 +133,8 @@ mha_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   uint64_t* o_full = bars + 8;
   uint64_t* o_empty = bars + 10;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + TMEM_PTR_OFF);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform values through a lane-0 shuffle: what derives from them stays in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int D = H * DH;
   constexpr bool has_last = LAST;               // token 256 exists
   const int Lk = has_last ? KP : L;             // keys held by the tensor-core tiles
@@ -162,7 +163,7 @@ mha_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ TMA producer
@@ -188,27 +189,37 @@ mha_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && n_my > 0) {
+    // The whole warp walks the loop and ONE elected lane issues the tcgen05 instructions, so their operands stay in
+    // uniform registers (under `if (lane == 0)` every MMA paid an ELECT / 4 x R2UR / retry-branch sequence of ~95
+    // cycles — three times the tensor-core time of a P.V MMA; measured on the ViT-B/16 kernel, attention_sm100_v2.cu).
+    if (n_my > 0) {
+      const bool elected = elect_one();
       constexpr uint32_t idesc_s = umma_idesc_bf16(QT, KP);
       constexpr uint32_t idesc_o = umma_idesc_bf16(QT, DH, /*b_mn_major=*/true);
       auto issue_s = [&](int x, int st) {
         const uint8_t* sb = smem + st * STAGE_BYTES;
         const uint64_t q_desc = umma_desc_sw128(sb + Q_OFF + x * (QT * 128));
         const uint64_t k_desc = umma_desc_sw128(sb + K_OFF);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16(tmem_base + x * TILE_COLS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[x]);
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16(tmem_base + x * TILE_COLS, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[x]);
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int x, int st) {
         const uint8_t* sb = smem + st * STAGE_BYTES;
         const uint64_t v_desc = umma_desc_sw128_mn(sb + V_OFF);
         const uint32_t t_tile = tmem_base + x * TILE_COLS;
+        if (elected) {
 #pragma unroll
-        for (int kk = 0; kk < KP / 16; ++kk)
-          umma_bf16_ts(t_tile + O_COL, t_tile + kk * 8, v_desc + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_o,
-                       kk != 0);
-        umma_commit(&o_full[x]);
+          for (int kk = 0; kk < KP / 16; ++kk)
+            umma_bf16_ts(t_tile + O_COL, t_tile + kk * 8, v_desc + static_cast<uint64_t>(kk) * (2048 >> 4), idesc_o,
+                         kk != 0);
+          umma_commit(&o_full[x]);
+        }
+        __syncwarp();
       };
       // issue order PV_A(i), S_A(i+1), PV_B(i), S_B(i+1), as in the v2 kernel
       mbar_wait(&load_full[0], 0);
@@ -232,7 +243,8 @@ mha_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         mbar_wait(&p_full[1], ph);
         tc_fence_after();
         issue_pv(1, st);
-        umma_commit(&stage_empty[st]);
+        if (elected) umma_commit(&stage_empty[st]);
+        __syncwarp();
         if (nxt) {
           mbar_wait(&o_empty[1], ph);
           tc_fence_after();

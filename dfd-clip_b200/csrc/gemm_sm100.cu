@@ -152,7 +152,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform values go through a lane-0 shuffle: the compiler then keeps what is derived from them (TMEM
+  // addresses, tile indices) in uniform registers, which the tcgen05 / TMA instructions take directly
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   const int num_m = (M + BM - 1) / BM;
@@ -184,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -204,7 +206,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop (uniform control flow, every lane polls the barriers) and ONE elected lane issues
+    // the tcgen05 instructions: under `if (lane == 0)` every operand lived in a vector register and each MMA paid an
+    // ELECT / R2UR.BROADCAST x 4 / retry-branch sequence (~95 cycles per issue, measured on the attention kernel).
+    {
+      const bool elected = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -219,15 +225,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint64_t a_desc = umma_desc_sw128(smem + OFF_A + stage * A_STAGE);
           const uint64_t b_desc = umma_desc_sw128(smem + OFF_B + stage * B_STAGE);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance both descriptors by k*32 bytes inside the 128-byte swizzle atom
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance both descriptors by k*32 bytes inside the 128-byte swizzle atom
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (elected) umma_commit(&tmem_full[acc]);  // accumulator complete
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -392,9 +402,11 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform values go through a lane-0 shuffle: the compiler then keeps what is derived from them (TMEM
+  // addresses, tile indices) in uniform registers, which the tcgen05 / TMA instructions take directly
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool leader = rank == 0;
 
   const int num_m2 = (M + 2 * BM - 1) / (2 * BM);
@@ -433,7 +445,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -456,7 +468,9 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // whole warp in the loop, one elected lane issues (see the 1-SM kernel): operands stay in uniform registers
+    if (leader) {
+      const bool elected = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -471,13 +485,17 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tc_fence_after();
           const uint64_t a_desc = umma_desc_sw128(smem + OFF_A + stage * A_STAGE);
           const uint64_t b_desc = umma_desc_sw128(smem + OFF_B + stage * B_STAGE);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage]);  // both CTAs' stage reusable once these MMAs retire
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);  // both CTAs' stage reusable once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tmem_full[acc]);  // accumulator complete in both CTAs' TMEM
+        if (elected) umma_commit_2sm(&tmem_full[acc]);  // accumulator complete in both CTAs' TMEM
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
