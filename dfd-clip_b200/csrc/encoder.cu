@@ -33,16 +33,19 @@ int fold_ln_linear(const float* W, const float* bias, const float* gamma, const 
                    float* bias_f, int N, int K, cudaStream_t stream);
 
 // LayerNorm folded into the GEMMs around it (see dfd_gemm_bf16_ln; the folding epilogues live in the SM-pair kernel,
-// which then runs for every M so that results do not depend on the batch size). OPT-IN with DFD_LN_FUSE=1: measured
-// on the power-capped B200 the removed LayerNorm passes (-1.65 ms per C2 step) are almost entirely paid back by the
-// heavier GEMM epilogues (+1.0 .. +1.4 ms), the step moves by 0 .. 1.7 %, so the separate
-// LayerNorm kernels stay the default.
-// DFD_LN_FUSE: 0 = separate LayerNorm kernels, 1 = ln_1 and ln_2 folded, 2 = only ln_1 folded (its producer is the
-// c_proj GEMM, K = 4D, whose epilogue has slack; ln_2 behind the short out-proj GEMM stays a kernel).
+// which then runs for every M so that results do not depend on the batch size). DFD_LN_FUSE selects:
+//   0  separate LayerNorm kernels (22 passes per C2 step, 1.8 ms);
+//   1  ln_1 AND ln_2 folded: no LayerNorm pass left (0.16 ms for ln_pre), but the out-proj GEMM (K = D, short
+//      mainloop) becomes epilogue-bound when it also has to emit bf16(x) and row statistics (164 -> 210 us);
+//   2  (default) only ln_1 folded: its producer is the c_proj GEMM (K = 4D), whose epilogue has slack; ln_2 behind
+//      the short out-proj GEMM stays a kernel.
+// Alternating A/B on one power-capped box (30 steps each, profiles/r2_lnfuse_ab.md): 17.64 / 17.23 / 17.23 ms per C2
+// step for modes 0 / 1 / 2; at the BASELINE-size goldens all three modes sit at max |dlogit| <= 3e-3 (tolerance 2e-2).
+// Mode 2 keeps the gain without slowing the out-proj GEMM.
 static int ln_fuse_mode() {
   static const int v = []() {
     const char* e = getenv("DFD_LN_FUSE");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 2;
   }();
   return v;
 }

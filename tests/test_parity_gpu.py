@@ -287,20 +287,23 @@ def test_full_size_c2_properties(cuda_device):
 
 
 @pytest.mark.gpu
-def test_parity_with_layernorm_folded_into_the_gemms(cuda_device):
-    """The opt-in encoder path DFD_LN_FUSE=1 (LayerNorm folded into the QKV / c_fc GEMM epilogues, residual GEMMs
-    emitting bf16(x) and row statistics) must meet the same golden-vector tolerances. The switch is read once per
-    process, so the golden-parity tests are re-run in a child process with it set."""
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_parity_with_the_other_layernorm_modes(cuda_device, mode):
+    """DFD_LN_FUSE selects how the encoder's LayerNorms run: 2 (default: ln_1 folded into the QKV GEMM's epilogue, its
+    producer c_proj emitting bf16(x) and row statistics), 1 (ln_2 folded as well), 0 (separate LayerNorm kernels). The
+    other two modes must meet the same golden-vector tolerances, at the small AND the BASELINE sizes. The switch is read
+    once per process, so the golden-parity tests are re-run in a child process with it set."""
     import os
     import subprocess
     import sys
-    if os.environ.get("DFD_LN_FUSE") == "1":
-        pytest.skip("already running with the folded path")
-    env = dict(os.environ, DFD_LN_FUSE="1")
+    if os.environ.get("DFD_LN_FUSE") is not None:
+        pytest.skip("already running with an explicit LayerNorm mode")
+    env = dict(os.environ, DFD_LN_FUSE=mode)
     here = os.path.dirname(os.path.abspath(__file__))
-    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_gpu.py"), "-q", "-m", "gpu",
-                          "-x", "-k", "golden or from_host or full_size"], env=env, capture_output=True, text=True,
-                         timeout=900)
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_gpu.py"),
+                          os.path.join(here, "test_fullsize_gpu.py"), "-q", "-m", "gpu", "-x", "-k",
+                          "golden or from_host or full_size or c2_64 or c4_vitl14 or c5_training"], env=env,
+                         capture_output=True, text=True, timeout=1500)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
 
 
