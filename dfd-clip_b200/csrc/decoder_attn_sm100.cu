@@ -167,34 +167,40 @@ dec_attn_stream_kernel(const float* __restrict__ qs, const __nv_bfloat16* __rest
       const int b = bt / T, t = bt % T;
       const int p_beg = half * p_half, p_end = min(P, p_beg + p_half);
 
-      // per-unit constants: (q0, q1) pairs, q1 - pe pairs, and the dot products of q0 / q1 with pe
-      u64 qp[16];    // (q0[c], q1[c])
-      u64 q1p2[8];   // (q1[c] - pe[c], q1[c+1] - pe[c+1])
+      // per-unit constants, all as pairs over two neighbouring channels (one bf16x2 word of a K / V row): q0, q1,
+      // q1 - pe, and the dot products of q0 / q1 with pe. Pairing over channels — not over (softmax, coda) — lets the
+      // unpacked halves of a word, which sit in adjacent registers, feed the packed FMAs without any register moves.
+      u64 q0p[8], q1p[8], q1mp[8];
       float c0 = 0.f, c1 = 0.f;
       const float* qh = qs + (static_cast<int64_t>(b) * H + head) * 128;
       const float* peh = pos_emb ? pos_emb + (static_cast<int64_t>(t) * H + head) * 64 : nullptr;
       {
-        float q1m[16];
+        float q0v[16], q1v[16], q1m[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float a = qh[chan(e)], bq = qh[64 + chan(e)];
           const float pv = peh ? peh[chan(e)] : 0.f;
-          qp[e] = pack2(a, bq);
+          q0v[e] = a;
+          q1v[e] = bq;
           q1m[e] = bq - pv;
           c0 = fmaf(a, pv, c0);
           c1 = fmaf(bq, pv, c1);
         }
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) q1p2[e >> 1] = pack2(q1m[e], q1m[e + 1]);
+        for (int e = 0; e < 16; e += 2) {
+          q0p[e >> 1] = pack2(q0v[e], q0v[e + 1]);
+          q1p[e >> 1] = pack2(q1v[e], q1v[e + 1]);
+          q1mp[e >> 1] = pack2(q1m[e], q1m[e + 1]);
+        }
 #pragma unroll
         for (int o = 1; o < 4; o <<= 1) {
           c0 += __shfl_xor_sync(0xffffffffu, c0, o);
           c1 += __shfl_xor_sync(0xffffffffu, c1, o);
         }
       }
-      u64 accp[16];  // (acc0[c], acc1[c])
+      u64 acc0p[8], acc1p[8];  // (acc[c], acc[c+1]) of the softmax / coda accumulators
 #pragma unroll
-      for (int e = 0; e < 16; ++e) accp[e] = 0ull;
+      for (int w = 0; w < 8; ++w) acc0p[w] = acc1p[w] = 0ull;
       float m = -INFINITY, l = 0.f, a1sum = 0.f;  // m in the log2 domain
       const u64 neg1 = pack2(-1.f, -1.f);
 
@@ -222,22 +228,22 @@ dec_attn_stream_kernel(const float* __restrict__ qs, const __nv_bfloat16* __rest
         for (int j = 0; j < 2; ++j) {
           // a pair may hold one valid token only (odd token count): the other half-warp contributes nothing
           const bool ok = valid[j];
-          u64 dpa = 0ull, dpb = 0ull;   // (q0.k, q1.k) partial sums
+          u64 dp0 = 0ull, dp1 = 0ull;   // q0.k and q1.k, each as (even channels, odd channels) partial sums
           float l1a = 0.f, l1b = 0.f;
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
             const uint32_t word = ok ? ((w < 4) ? (&kraw[j][0].x)[w] : (&kraw[j][1].x)[w - 4]) : 0u;
-            const float klo = __uint_as_float(word << 16), khi = __uint_as_float(word & 0xffff0000u);
-            dpa = fma2(pack2(klo, klo), qp[2 * w], dpa);
-            dpb = fma2(pack2(khi, khi), qp[2 * w + 1], dpb);
+            const u64 kk = pack2(__uint_as_float(word << 16), __uint_as_float(word & 0xffff0000u));
+            dp0 = fma2(kk, q0p[w], dp0);
+            dp1 = fma2(kk, q1p[w], dp1);
             float dlo, dhi;
-            unpack2(fma2(pack2(klo, khi), neg1, q1p2[w]), dlo, dhi);  // (q1 - pe) - k
+            unpack2(fma2(kk, neg1, q1mp[w]), dlo, dhi);  // (q1 - pe) - k
             l1a += fabsf(dlo);
             l1b += fabsf(dhi);
           }
-          float d0a, d1a, d0b, d1b;
-          unpack2(dpa, d0a, d1a);
-          unpack2(dpb, d0b, d1b);
+          float d0a, d0b, d1a, d1b;
+          unpack2(dp0, d0a, d0b);
+          unpack2(dp1, d1a, d1b);
           float d0s = d0a + d0b, d1s = d1a + d1b, l1s = l1a + l1b;
 #pragma unroll
           for (int o = 1; o < 4; o <<= 1) {
@@ -256,13 +262,13 @@ dec_attn_stream_kernel(const float* __restrict__ qs, const __nv_bfloat16* __rest
           const float gate = __fdividef(2.f, 1.f + fast_exp2(l1s * (0.125f * kLog2e)));
           const float a1 = ok ? tanh_fast((d1s + c1) * 0.125f) * gate : 0.f;
           a1sum += a1;
-          const u64 wp = pack2(pr, a1), rp = pack2(resc, 1.f);
+          const u64 prp = pack2(pr, pr), a1p = pack2(a1, a1), rp = pack2(resc, resc);
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
             const uint32_t word = ok ? ((w < 4) ? (&vraw[j][0].x)[w] : (&vraw[j][1].x)[w - 4]) : 0u;
-            const float vlo = __uint_as_float(word << 16), vhi = __uint_as_float(word & 0xffff0000u);
-            accp[2 * w] = fma2(accp[2 * w], rp, mul2(pack2(vlo, vlo), wp));
-            accp[2 * w + 1] = fma2(accp[2 * w + 1], rp, mul2(pack2(vhi, vhi), wp));
+            const u64 vv = pack2(__uint_as_float(word << 16), __uint_as_float(word & 0xffff0000u));
+            acc0p[w] = fma2(acc0p[w], rp, mul2(vv, prp));   // online softmax: rescale, then add p * v
+            acc1p[w] = fma2(vv, a1p, acc1p[w]);             // coda: plain accumulation
           }
         }
       }
@@ -277,11 +283,14 @@ dec_attn_stream_kernel(const float* __restrict__ qs, const __nv_bfloat16* __rest
         m = mn;
         a1sum += __shfl_xor_sync(0xffffffffu, a1sum, 16);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float x0, x1;
-          unpack2(accp[e], x0, x1);
-          acc0[e] = x0 * sa + __shfl_xor_sync(0xffffffffu, x0, 16) * sb;
-          acc1[e] = x1 + __shfl_xor_sync(0xffffffffu, x1, 16);
+        for (int w = 0; w < 8; ++w) {
+          float x0, x1, y0, y1;
+          unpack2(acc0p[w], x0, x1);
+          unpack2(acc1p[w], y0, y1);
+          acc0[2 * w] = x0 * sa + __shfl_xor_sync(0xffffffffu, x0, 16) * sb;
+          acc0[2 * w + 1] = x1 * sa + __shfl_xor_sync(0xffffffffu, x1, 16) * sb;
+          acc1[2 * w] = y0 + __shfl_xor_sync(0xffffffffu, y0, 16);
+          acc1[2 * w + 1] = y1 + __shfl_xor_sync(0xffffffffu, y1, 16);
         }
       }
       // V + pe: sum a (V + pe) = sum a V + (sum a) pe
