@@ -111,13 +111,15 @@ static PackedLayout packed_layout(const VitShape& s) {
   p.ln1_b = ltake(D * 4);
   p.ln2_w = ltake(D * 4);
   p.ln2_b = ltake(D * 4);
-  if (ln_fuse_enabled()) {  // the folded copies exist only when the opt-in path is selected
+  if (ln_fuse_enabled()) {  // folded copy of in_proj (ln_1); of c_fc (ln_2) only when both LayerNorms are folded
     p.wf_in = ltake(3 * D * D * 2);
-    p.wf_fc = ltake(4 * D * D * 2);
     p.c_in = ltake(3 * D * 4);
-    p.c_fc = ltake(4 * D * 4);
     p.bf_in = ltake(3 * D * 4);
-    p.bf_fc = ltake(4 * D * 4);
+    if (ln_fuse_mode() == 1) {
+      p.wf_fc = ltake(4 * D * D * 2);
+      p.c_fc = ltake(4 * D * 4);
+      p.bf_fc = ltake(4 * D * 4);
+    }
   }
   p.layer_stride = lo;
   p.total = p.layer0 + p.layer_stride * s.layers;
@@ -188,10 +190,11 @@ int encoder_pack_weights(const dfd_ctx* ctx, const dfd_vit_dims* dims, const dfd
     DFD_TRY(copy_f32(lb + pl.ln2_w, w->ln_2_weight[l], D));
     DFD_TRY(copy_f32(lb + pl.ln2_b, w->ln_2_bias[l], D));
     if (!ln_fuse_enabled()) continue;
-    // ln_1 folded into in_proj, ln_2 folded into c_fc
+    // ln_1 folded into in_proj; ln_2 folded into c_fc in mode 1
     DFD_TRY(fold_ln_linear(w->in_proj_weight[l], w->in_proj_bias[l], w->ln_1_weight[l], w->ln_1_bias[l],
                            base + lb + pl.wf_in, reinterpret_cast<float*>(base + lb + pl.c_in),
                            reinterpret_cast<float*>(base + lb + pl.bf_in), 3 * s.D, s.D, stream));
+    if (ln_fuse_mode() != 1) continue;
     DFD_TRY(fold_ln_linear(w->c_fc_weight[l], w->c_fc_bias[l], w->ln_2_weight[l], w->ln_2_bias[l],
                            base + lb + pl.wf_fc, reinterpret_cast<float*>(base + lb + pl.c_fc),
                            reinterpret_cast<float*>(base + lb + pl.bf_fc), 4 * s.D, s.D, stream));

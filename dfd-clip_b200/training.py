@@ -244,30 +244,44 @@ class TrainStep:
         main = torch.cuda.current_stream(self.dev)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.dev)
+            with torch.cuda.stream(self._copy_stream):   # two staging sets, owned by the copy stream's allocator pool
+                self._staging = [[torch.empty_like(t) for t in (self.x, self.y, self.m)] for _ in range(2)]
+            self._staged_free = [None, None]             # event: the step has copied the slot into its static buffers
         copy = self._copy_stream
 
-        def issue(batch):
+        def issue(slot, batch):
             with torch.cuda.stream(copy):
-                bufs = [t.to(self.dev, non_blocking=True) for t in batch]
+                if self._staged_free[slot] is not None:
+                    copy.wait_event(self._staged_free[slot])
+                for dst, src in zip(self._staging[slot], batch):
+                    dst.copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
-            return bufs, ev
+            return slot, ev
 
         it = iter(batches)
         try:
-            nxt = issue(next(it))
+            nxt = issue(0, next(it))
         except StopIteration:
             return
+        k = 0
         while nxt is not None:
-            cur = nxt
+            slot, ev = nxt
+            k += 1
             try:
-                nxt = issue(next(it))   # in flight while this step runs
+                nxt = issue(k % 2, next(it))   # in flight while this step runs
             except StopIteration:
                 nxt = None
-            main.wait_event(cur[1])
-            for t in cur[0]:
-                t.record_stream(main)   # allocated on the copy stream, consumed on this one
-            yield self(*cur[0])
+            main.wait_event(ev)
+            self._load(*self._staging[slot], None if self.speed is None else self.speed)
+            free = torch.cuda.Event()
+            free.record(main)
+            self._staged_free[slot] = free
+            if self.graph is None:
+                self.loss, self.logits = self._body()
+            else:
+                self.graph.replay()
+            yield self.loss, self.logits
 
     def eager(self, x, y, m, speed=None):
         """The same step without the graph (per-kernel timing, debugging)."""

@@ -40,8 +40,37 @@ def check_logits(got, ref):
     assert np.array_equal(got[ok].argmax(-1)[gap > 4 * TOL_LOGIT_ABS], ref[ok].argmax(-1)[gap > 4 * TOL_LOGIT_ABS])
 
 
-@pytest.mark.parametrize("case", ["tiny_aug_query", "tiny_global_pred", "small_gp_aq", "tiny_no_tpos",
-                                  "tiny_attn_frame", "tiny_attn_tf", "small_attn_temporal"])
+@pytest.mark.parametrize("case", ["tiny_attn_frame", "tiny_attn_tf", "small_attn_temporal"])
+def test_attn_modes_match_reference_golden(cuda_device, case):
+    """op_mode.attn_mode (src/models.py:107-115): softmax per frame and / or across frames instead of over all T*P keys.
+    On the toy architectures these groups hold 4 patches (tiny: 32-pixel frames) or 3 frames: a softmax over that few
+    keys does not average the bf16 rounding of the encoder taps, and 5 l / |l| then moves the logits by up to ~3e-2
+    for ANY bf16 tap rounding (the three LayerNorm modes, whose projections have the same 2.3e-3 relative error —
+    tools/ln_fold_numerics.py — land at 1.2e-2 / 3.5e-2 / 3.5e-2 here while agreeing to 2e-3 at ViT-B/16, C2). So, as
+    for patch_mask + adapter below: everything after the encoder — mode kernels, decoder, normalisation — is pinned at
+    the north_star tolerance against the oracle evaluated on the GPU's own taps, the video feature at the feature
+    tolerance, and the golden logits end to end at 3x the tolerance."""
+    oracle = load_oracle()
+    g = load_golden(case)
+    sd, x, m = golden_inputs(g)
+    det = build_mode_detector(g, cuda_device, sd)
+    logits, feats = det.predict(x.to(cuda_device), m.to(cuda_device), with_video_features=True)
+    torch.cuda.synchronize()
+    got = logits[0].cpu().numpy()
+    b, t = x.shape[:2]
+    qkv, _ = det.encoder.encode(x.flatten(0, 1).to(cuda_device), keep_layers=det.layer_indices)
+    kvs = [{n: kv[n].float().cpu() for n in kv} for kv in det.taps_from_qkv(qkv, b, t)]
+    mode = tuple(golden_op_mode(g)["attn_mode"].split("+"))
+    raw, feat, _ = oracle.decoder_forward(sd, kvs, m, (2,), layer_indices=g["layer_indices"], attn_mode=mode)
+    check_logits(got, oracle.normalise_logits(raw)[0].numpy())
+    ok = ~torch.isnan(feat.flatten(1)).any(1)
+    assert cosine(feats["video"].cpu()[ok], feat[ok]) >= TOL_FEATURE_COSINE
+    assert np.array_equal(np.isnan(got), np.isnan(g["logits"]))
+    assert np.nanmax(np.abs(got - g["logits"])) <= 3 * TOL_LOGIT_ABS
+    assert cosine(feats["video"].cpu()[ok], torch.from_numpy(g["video_feature"])[ok]) >= 0.998
+
+
+@pytest.mark.parametrize("case", ["tiny_aug_query", "tiny_global_pred", "small_gp_aq", "tiny_no_tpos"])
 def test_op_modes_match_reference_golden(cuda_device, case):
     g = load_golden(case)
     sd, x, m = golden_inputs(g)
