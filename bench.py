@@ -77,8 +77,15 @@ def flops_per_clip(dims, frames, taps, executed=True):
 
 
 def launches_per_predict(layers_run_full, n_taps, n_tasks, adapter=False):
-    enc = 4 + 7 * layers_run_full + 2
-    dec = 2 + 9 * n_taps + 1 + n_tasks
+    """Kernels of this library per Detector.predict. Encoder: patchify, patch GEMM, ln_pre; per full layer QKV GEMM,
+    attention, out-proj GEMM, ln_2, c_fc GEMM, c_proj GEMM (+ ln_1 unless it is folded into the QKV GEMM, the default;
+    ln_2 is folded too with DFD_LN_FUSE=1); the last tapped layer only its K/V projection (+ ln_1). Decoder: ln_pre +
+    broadcast, per block 2 LayerNorms, 4 linears of 2 kernels, attention stream + combine, block-output scatter; ln_post;
+    one projection kernel per task."""
+    mode = os.environ.get("DFD_LN_FUSE", "2")
+    ln_per_layer = {"0": 2, "1": 0}.get(mode, 1)
+    enc = 3 + (5 + ln_per_layer) * layers_run_full + 1 + (1 if mode == "0" else 0)
+    dec = 2 + 13 * n_taps + 1 + n_tasks
     return enc + dec + (6 * n_taps if adapter else 0)  # adapter: down GEMM, norm/act kernel, up GEMM per k and v
 
 
