@@ -859,30 +859,31 @@ class Detector(nn.Module):
         return task_logits, features
 
     def _mask_patches(self, kvs):
-        """train_mode.patch_mask (reference :511-544): keep a random subset of the patch positions, drawn with numpy's
-        global RNG exactly like the reference ("batch": one draw shared by all layers, "sample": one per layer,
-        "guide": one per layer weighted by the guide map). The gathered K/V are compact bf16 tensors that the native
-        decoder attention streams through their own strides."""
+        """train_mode.patch_mask (reference :511-544): the decoder sees a random subset of the patch positions. The
+        subset comes from numpy's global RNG with the reference's draw sequence so that a seeded run selects the same
+        patches: "batch" draws once for all tapped layers, "sample" once per layer, "guide" once per layer with the
+        guide map of that layer as the probabilities. The gathered K/V are compact bf16 tensors that the native decoder
+        attention streams through their own strides."""
         import numpy as np
         cfg = self.train_mode.patch_mask
-        num_patch = kvs[0]["k"].shape[2]
-        num_select = int(num_patch * cfg.ratio)
-        patch_indices = None
-        out = []
-        for i, kv in enumerate(kvs):
-            if cfg.type == "batch":
-                if patch_indices is None:
-                    patch_indices = np.random.choice(range(num_patch), num_select, replace=False)
-            elif cfg.type == "sample":
-                patch_indices = np.random.choice(range(num_patch), num_select, replace=False)
-            elif cfg.type == "guide":
-                patch_indices = np.random.choice(range(num_patch), num_select, replace=False,
-                                                 p=self.guide_map["v"][self.layer_indices[i]].flatten())
-            else:
-                raise NotImplementedError()
-            idx = torch.as_tensor(np.asarray(patch_indices), dtype=torch.long, device=kv["k"].device)
-            out.append({n: kv[n].index_select(2, idx) for n in kv})
-        return out
+        if cfg.type not in ("batch", "sample", "guide"):
+            raise NotImplementedError()
+        n_patch = kvs[0]["k"].shape[2]
+        n_keep = int(n_patch * cfg.ratio)
+
+        def draw(layer):
+            weights = self.guide_map["v"][self.layer_indices[layer]].flatten() if cfg.type == "guide" else None
+            if weights is None:
+                return np.random.choice(range(n_patch), n_keep, replace=False)
+            return np.random.choice(range(n_patch), n_keep, replace=False, p=weights)
+
+        shared = draw(0) if cfg.type == "batch" else None
+        masked = []
+        for layer, kv in enumerate(kvs):
+            keep = shared if shared is not None else draw(layer)
+            idx = torch.as_tensor(np.asarray(keep), dtype=torch.long, device=kv["k"].device)
+            masked.append({name: t.index_select(2, idx) for name, t in kv.items()})
+        return masked
 
     def forward(self, x, y, m, comp=None, speed=None, train=False, single_task=None, *args, **kargs):
         """Eval: ``(task_losses, task_logits)``; train adds ``other_losses`` (reference :568-596, 738)."""
@@ -904,41 +905,41 @@ class Detector(nn.Module):
         return task_losses, task_logits, self._auxiliary_losses(video_features, speed, b)
 
     def _auxiliary_losses(self, video_features, speed, b):
-        """The trainer's extra term that the reference can execute (reference :676-736): ``train_mode.temporal``, a
-        speed ranking / triplet loss in plain torch on the [B, D] video features."""
+        """``train_mode.temporal`` (reference :676-736; SURVEY marks it out of scope — kept from round 1, not extended):
+        a speed term on the [B, D] video features, evaluated in closed form on index tensors.
+
+        * ``ranking``: hinge ``max(0, s_j - s_i)`` over every pair whose speeds are ordered ``speed_i > speed_j`` (the
+          reference's margin-ranking loss with target 1, margin 0), mean over the B(B-1)/2 pairs, times 0.05;
+        * ``triplet``: up to ten clip triples — the first 3-combinations of a ``random.shuffle`` of the batch, the
+          reference's draw — ordered by speed (fast, mid, slow); two Euclidean triplet terms per triple, anchored at
+          the fast and at the slow clip, with the speed gaps as margins; times 0.01 / (2 * rounds)."""
+        if "temporal" not in self.train_mode:
+            return {}
+        kind = self.train_mode.temporal
+        order = torch.argsort(speed, descending=True)
+        if kind == "ranking":
+            scores = (video_features @ self.ranking_transform_param).reshape(-1)[order]  # fastest clip first
+            hi, lo = torch.triu_indices(b, b, offset=1, device=scores.device)
+            return {"speed/rank": 0.05 * torch.relu(scores[lo] - scores[hi]).mean()}
+        if kind != "triplet":
+            raise NotImplementedError()
         import random
-        from itertools import combinations
-        from math import comb as n_choose
-        device = video_features.device
-        other_losses = {}
-        if "temporal" in self.train_mode:
-            speed_rank_index = torch.argsort(speed, descending=True).tolist()
-            speed_loss = torch.tensor(0.0, device=device)
-            if self.train_mode.temporal == "ranking":
-                rank_logits = (video_features @ self.ranking_transform_param).squeeze()
-                rank_losses = []
-                for rank in range(0, b - 1):
-                    input1 = rank_logits[speed_rank_index[rank]].repeat(b - 1 - rank)
-                    input2 = rank_logits[speed_rank_index[rank + 1:], ...]
-                    target = torch.ones(b - 1 - rank, device=device)
-                    rank_losses.append(torch.nn.functional.margin_ranking_loss(input1, input2, target,
-                                                                               reduction="none"))
-                other_losses["speed/rank"] = 0.05 * torch.cat(rank_losses).mean()
-            else:  # "triplet"
-                margin_rounds = min(n_choose(b, 3), 10)
-                indices = list(range(b))
-                random.shuffle(indices)
-                triples = iter(combinations(indices, 3))
-                for _ in range(margin_rounds):
-                    b_index = sorted(next(triples), key=lambda _i: speed_rank_index.index(_i))
-                    speed_loss = speed_loss + torch.nn.functional.triplet_margin_loss(
-                        anchor=video_features[b_index[0]], positive=video_features[b_index[1]],
-                        negative=video_features[b_index[2]], margin=torch.abs(speed[b_index[2]] - speed[b_index[1]]))
-                    speed_loss = speed_loss + torch.nn.functional.triplet_margin_loss(
-                        anchor=video_features[b_index[2]], positive=video_features[b_index[1]],
-                        negative=video_features[b_index[0]], margin=torch.abs(speed[b_index[1]] - speed[b_index[0]]))
-                other_losses["speed/triplet"] = 0.01 * speed_loss / (margin_rounds * 2)
-        return other_losses
+        from itertools import combinations, islice
+        from math import comb
+        rounds = min(comb(b, 3), 10)
+        place = {clip: rank for rank, clip in enumerate(order.tolist())}
+        shuffled = list(range(b))
+        random.shuffle(shuffled)
+        triples = [sorted(tr, key=place.__getitem__) for tr in islice(combinations(shuffled, 3), rounds)]
+        fast, mid, slow = torch.tensor(triples, dtype=torch.long, device=video_features.device).unbind(1)
+
+        def dist(i, j):  # torch's pairwise_distance: the eps is added to the difference
+            return (video_features[i] - video_features[j] + 1e-6).norm(dim=-1)
+
+        d_fm, d_fs, d_sm = dist(fast, mid), dist(fast, slow), dist(slow, mid)
+        gap_ms, gap_fm = (speed[slow] - speed[mid]).abs(), (speed[mid] - speed[fast]).abs()
+        total = torch.relu(d_fm - d_fs + gap_ms).sum() + torch.relu(d_sm - d_fs + gap_fm).sum()
+        return {"speed/triplet": 0.01 * total / (rounds * 2)}
 
     def configure_optimizers(self, lr):
         params = [i for i in self.parameters() if i.requires_grad]
