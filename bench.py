@@ -701,14 +701,21 @@ def run_c5(args, rank, world, local_rank):
     step_ms = elapsed_ms / args.steps
     value = world * clips * args.steps / (elapsed_ms * 1e-3)
     # end to end: every step's batch comes from pinned host memory and its loss goes back to the host
+    for loss, _ in step.run_host((x_host, y_host, m_host) for _ in range(3)):   # untimed: copy stream, staging buffers
+        loss.item()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    stamps = []
     for loss, _ in step.run_host((x_host, y_host, m_host) for _ in range(args.steps)):
         loss_host = loss.item()
+        stamps.append(time.perf_counter())
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0, dev, dist)
+    gaps = sorted((b - a) * 1e3 for a, b in zip([t0] + stamps, stamps))
+    print("c5 e2e: per-step host time min %.2f / median %.2f / max %.2f ms" % (gaps[0], gaps[len(gaps) // 2], gaps[-1]),
+          file=sys.stderr)
     same = True
     if dist:  # replicas must stay identical
         chk = torch.stack([p.detach().double().sum() for p in det.decoder.parameters()]).sum().reshape(1)
@@ -718,6 +725,8 @@ def run_c5(args, rank, world, local_rank):
         same = bool((lo == hi).item())
     # roofline of the encoder GEMMs inside the step: an eager (un-graphed) pass of the same step with launch events
     kernel_ms = timed_kernels(dev, lambda: step.eager(x, y, m), 3)
+    description, launches = step.describe(), step.launches_per_step
+    step.close()   # the graph holds captured NCCL plans: it must go before the process group does
     if rank != 0:
         return
     peaks = load_peaks()
@@ -733,12 +742,12 @@ def run_c5(args, rank, world, local_rank):
         if world > 1 else "none (1 GPU)", "replicas_identical": same, "final_loss": loss_host,
         "l2": "flushed_by_the_step (each step streams %.0f MB of taps and %.0f MB of parameters, gradients and "
               "momentum, far more than L2)" % (2 * clips * frames * 196 * 768 * 2 * len(taps) / 1e6, n_grad * 12 / 1e6),
-        "flops_per_clip_executed": total_flops, "step": step.describe()}
+        "flops_per_clip_executed": total_flops, "step": description}
     line["e2e"] = {"value": world * clips * args.steps / dt, "unit": UNIT,
                    "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8 + m_host.numel(),
                    "d2h_bytes_per_step": 4, "api": "dfdclip_b200.training.TrainStep.run_host: pinned host batches, the "
                    "H2D copy of batch k+1 overlaps step k, loss.item() per step"}
-    line["gpu_launches"] = step.launches_per_step * args.steps
+    line["gpu_launches"] = launches * args.steps
     line["roofline"] = roofline_block(args, dims, taps, kernel_ms, clips, step_ms, peaks)
     line["cpu_baseline"] = cpu_baseline(args) if world == 1 and not args.no_cpu_baseline else None
     emit(line)
@@ -803,11 +812,19 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    done = False
     try:
         {"c3": run_c3, "c5": run_c5}.get(args.workload, run_predict)(args, rank, world, local_rank)
+        done = True
     finally:
         if world > 1 and torch.distributed.is_initialized():
+            # the result line is out; a communicator teardown that does not finish must not hold the box
+            guard = threading.Timer(60.0, lambda: os._exit(0 if done else 1))
+            guard.daemon = True
+            guard.start()
+            torch.cuda.synchronize()
             torch.distributed.destroy_process_group()
+            guard.cancel()
 
 
 if __name__ == "__main__":

@@ -30,7 +30,7 @@ EXPORTS = (
     "dfd_patchify_u8", "dfd_encoder_forward_u8", "dfd_gemm_bf16_ln", "dfd_predict_forward",
     "dfd_linear_f32_workspace_bytes", "dfd_linear_f32",
     "dfd_resize_crop_u8_workspace_bytes", "dfd_resize_crop_u8",
-    "dfd_decoder_train_bytes", "dfd_decoder_train_forward", "dfd_decoder_train_backward",
+    "dfd_decoder_train_bytes", "dfd_decoder_train_forward", "dfd_decoder_train_backward", "dfd_train_forward",
     "dfd_linear_f32_backward_workspace_bytes", "dfd_linear_f32_backward",
 )
 
@@ -134,6 +134,11 @@ def load_library():
                                             c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
                                             ctypes.POINTER(KvTaps), ctypes.POINTER(c_int), c_void_p, c_int, c_int,
                                             c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]
+        lib.dfd_train_forward.argtypes = [c_void_p, ctypes.POINTER(VitDims), c_void_p, c_void_p, c_int,
+                                          ctypes.POINTER(c_float), c_int, c_int, c_int, _PP, c_void_p, c_size_t,
+                                          c_int, c_int, c_int, ctypes.POINTER(DecoderWeights),
+                                          ctypes.POINTER(KvTaps), ctypes.POINTER(c_int), c_void_p, c_int, c_int,
+                                          c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]
         lib.dfd_project_logits.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                            c_void_p]
         lib.dfd_linear_f32_workspace_bytes.argtypes = [c_int, c_int]

@@ -265,9 +265,10 @@ size_t linear_bwd_workspace_bytes(int B, int max_n, int max_k) {
 }
 
 // dx = (dy W) [* quickgelu'(gelu_pre)] [+ dx_add]; dW = dy^T x; db = column sums of dy. Any output may be NULL.
+// dw_stream: the stream of the weight-gradient kernel (independent of the dx chain); NULL = `stream`.
 int linear_f32_backward(const dfd_ctx* ctx, const float* x, const float* W, const float* dy, const float* gelu_pre,
                         const float* dx_add, float* dx, float* dW, float* db, int B, int N, int K, float* part,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, cudaStream_t dw_stream = nullptr) {
   DFD_CHECK_ARG(K % 4 == 0, "linear_f32_backward: K=%d must be a multiple of 4", K);
   if (dx) {
     const int splits = (N + DX_NC - 1) / DX_NC;
@@ -281,7 +282,7 @@ int linear_f32_backward(const dfd_ctx* ctx, const float* x, const float* W, cons
   }
   if (dW) {
     dim3 grid((K + DW_KT - 1) / DW_KT, (N + DW_NT - 1) / DW_NT);
-    lin_dw_kernel<<<grid, 256, 0, stream>>>(dy, x, dW, db, B, N, K);
+    lin_dw_kernel<<<grid, 256, 0, dw_stream ? dw_stream : stream>>>(dy, x, dW, db, B, N, K);
     DFD_CUDA_OK(cudaGetLastError());
   }
   (void)ctx;
@@ -341,56 +342,68 @@ static int check_train_args(int D, int H, int n_blocks, const dfd_decoder_weight
   return 0;
 }
 
-int decoder_train_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
-                          const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
-                          void* saved, size_t saved_bytes, cudaStream_t stream) {
+int DecoderTrainRun::begin(cudaStream_t stream) {
   const TrainBuf tb = train_layout(B, T, D, H, n_blocks);
   DFD_TRY(check_train_args(D, H, n_blocks, w, taps, mask, B, T, P, saved, saved_bytes, tb));
   DFD_CHECK_ARG(block_out != nullptr, "decoder_train_forward: block_out is NULL");
   uint8_t* base = static_cast<uint8_t*>(saved);
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
-  const size_t BD = static_cast<size_t>(B) * D;
-  float* lin = F(tb.lin);
   // x0 = ln_pre(class_embedding) for every clip (models.py:336-337), written as block 0's input
   ln_rows_fwd_kernel<<<B, 256, 0, stream>>>(w->class_embedding, 0, w->ln_pre_weight, w->ln_pre_bias, F(tb.x_in),
                                             F(tb.st_pre), D);
   DFD_CUDA_OK(cudaGetLastError());
-  for (int i = 0; i < n_blocks; ++i) {
-    const size_t bo = tb.blk_stride * i;
-    float *x_in = F(bo + tb.x_in), *y1 = F(bo + tb.y1), *qs = F(bo + tb.qs), *mix = F(bo + tb.mix),
-          *x1 = F(bo + tb.x1), *y2 = F(bo + tb.y2), *hpre = F(bo + tb.hpre), *h = F(bo + tb.h);
-    if (i > 0 && w->augment_query) {  // models.py:265-267: added after the block output has been recorded
-      DFD_CHECK_ARG(w->augment_query[i - 1] != nullptr, "decoder_train: augment_query[%d] is NULL", i - 1);
-      add_rows_kernel<<<(static_cast<int>(BD) + 255) / 256, 256, 0, stream>>>(x_in, w->augment_query[i - 1], B, D);
-      DFD_CUDA_OK(cudaGetLastError());
-    }
-    {
-      ScopedTimer _t(ctx, DFD_TAG_DEC_OTHER, stream);
-      ln_rows_fwd_kernel<<<B, 256, 0, stream>>>(x_in, D, w->ln_1_weight[i], w->ln_1_bias[i], y1, F(bo + tb.st1), D);
-      DFD_CUDA_OK(cudaGetLastError());
-    }
-    DFD_TIMED(DFD_TAG_DEC_LINEAR,
-              linear_f32(ctx, y1, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, qs, B, 2 * D, D, false, lin, stream));
-    DFD_TIMED(DFD_TAG_DEC_ATTN,
-              decoder_attention(ctx, qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
-                                w->positional_embedding, mask, B, T, P, H, mix, F(tb.attn),
-                                dec_attn_workspace_bytes(B, T, H), stream, F(bo + tb.ast)));
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, mix, w->out_proj_weight[i], w->out_proj_bias[i], x_in, x1, B, D, D,
-                                             false, lin, stream));
-    {
-      ScopedTimer _t(ctx, DFD_TAG_DEC_OTHER, stream);
-      ln_rows_fwd_kernel<<<B, 256, 0, stream>>>(x1, D, w->ln_2_weight[i], w->ln_2_bias[i], y2, F(bo + tb.st2), D);
-      DFD_CUDA_OK(cudaGetLastError());
-    }
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, y2, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, h, B, 4 * D, D, true,
-                                             lin, stream, hpre));
-    // the block output is the next block's input (dense, saved for its backward) and row i of block_out (strided)
-    float* x2 = (i + 1 < n_blocks) ? F(bo + tb.blk_stride + tb.x_in) : F(tb.dx);
-    DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, h, w->c_proj_weight[i], w->c_proj_bias[i], x1, x2, B, D, 4 * D, false,
-                                             lin, stream));
-    DFD_CUDA_OK(cudaMemcpy2DAsync(block_out + static_cast<size_t>(i) * D, static_cast<size_t>(n_blocks) * D * sizeof(float),
-                                  x2, D * sizeof(float), D * sizeof(float), B, cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+int DecoderTrainRun::block(int i, cudaStream_t stream) {
+  const TrainBuf tb = train_layout(B, T, D, H, n_blocks);
+  uint8_t* base = static_cast<uint8_t*>(saved);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const size_t BD = static_cast<size_t>(B) * D;
+  float* lin = F(tb.lin);
+  const size_t bo = tb.blk_stride * i;
+  float *x_in = F(bo + tb.x_in), *y1 = F(bo + tb.y1), *qs = F(bo + tb.qs), *mix = F(bo + tb.mix), *x1 = F(bo + tb.x1),
+        *y2 = F(bo + tb.y2), *hpre = F(bo + tb.hpre), *h = F(bo + tb.h);
+  if (i > 0 && w->augment_query) {  // models.py:265-267: added after the block output has been recorded
+    DFD_CHECK_ARG(w->augment_query[i - 1] != nullptr, "decoder_train: augment_query[%d] is NULL", i - 1);
+    add_rows_kernel<<<(static_cast<int>(BD) + 255) / 256, 256, 0, stream>>>(x_in, w->augment_query[i - 1], B, D);
+    DFD_CUDA_OK(cudaGetLastError());
   }
+  {
+    ScopedTimer _t(ctx, DFD_TAG_DEC_OTHER, stream);
+    ln_rows_fwd_kernel<<<B, 256, 0, stream>>>(x_in, D, w->ln_1_weight[i], w->ln_1_bias[i], y1, F(bo + tb.st1), D);
+    DFD_CUDA_OK(cudaGetLastError());
+  }
+  DFD_TIMED(DFD_TAG_DEC_LINEAR,
+            linear_f32(ctx, y1, w->in_proj_weight[i], w->in_proj_bias[i], nullptr, qs, B, 2 * D, D, false, lin, stream));
+  DFD_TIMED(DFD_TAG_DEC_ATTN,
+            decoder_attention(ctx, qs, taps->k[i], taps->v[i], taps->stride_b, taps->stride_t, taps->stride_p,
+                              w->positional_embedding, mask, B, T, P, H, mix, F(tb.attn),
+                              dec_attn_workspace_bytes(B, T, H), stream, F(bo + tb.ast)));
+  DFD_TIMED(DFD_TAG_DEC_LINEAR,
+            linear_f32(ctx, mix, w->out_proj_weight[i], w->out_proj_bias[i], x_in, x1, B, D, D, false, lin, stream));
+  {
+    ScopedTimer _t(ctx, DFD_TAG_DEC_OTHER, stream);
+    ln_rows_fwd_kernel<<<B, 256, 0, stream>>>(x1, D, w->ln_2_weight[i], w->ln_2_bias[i], y2, F(bo + tb.st2), D);
+    DFD_CUDA_OK(cudaGetLastError());
+  }
+  DFD_TIMED(DFD_TAG_DEC_LINEAR, linear_f32(ctx, y2, w->c_fc_weight[i], w->c_fc_bias[i], nullptr, h, B, 4 * D, D, true,
+                                           lin, stream, hpre));
+  // the block output is the next block's input (dense, saved for its backward) and row i of block_out (strided)
+  float* x2 = (i + 1 < n_blocks) ? F(bo + tb.blk_stride + tb.x_in) : F(tb.dx);
+  DFD_TIMED(DFD_TAG_DEC_LINEAR,
+            linear_f32(ctx, h, w->c_proj_weight[i], w->c_proj_bias[i], x1, x2, B, D, 4 * D, false, lin, stream));
+  DFD_CUDA_OK(cudaMemcpy2DAsync(block_out + static_cast<size_t>(i) * D, static_cast<size_t>(n_blocks) * D * sizeof(float),
+                                x2, D * sizeof(float), D * sizeof(float), B, cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+int decoder_train_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
+                          const dfd_kv_taps* taps, const uint8_t* mask, int B, int T, int P, float* block_out,
+                          void* saved, size_t saved_bytes, cudaStream_t stream) {
+  DecoderTrainRun run{ctx, D, H, n_blocks, w, taps, mask, B, T, P, block_out, saved, saved_bytes};
+  DFD_TRY(run.begin(stream));
+  for (int i = 0; i < n_blocks; ++i) DFD_TRY(run.block(i, stream));
   return 0;
 }
 
@@ -400,10 +413,32 @@ int decoder_train_forward(const dfd_ctx* ctx, int D, int H, int n_blocks, const 
 // blocks (all-reduce a finished block's gradients while the next block's backward runs) walks from n_blocks - 1 down
 // to 0 in several calls: the gradient in flight lives in `saved`. positional_embedding's gradient is complete, and
 // class_embedding / ln_pre gradients are written, by the call that includes block 0.
-int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
-                           const dfd_decoder_weights* grads, const dfd_kv_taps* taps, const uint8_t* mask, int B, int T,
-                           int P, const float* d_block_out, float* const* dk, float* const* dv, void* saved,
-                           size_t saved_bytes, int block_hi, int block_lo, cudaStream_t stream) {
+// The weight gradients (dW = dy^T x, rank-B outer products: 26 MB written per block) do not feed the chain
+// dx2 -> dh -> dy2 -> dx1 -> dmix -> dqs -> dy1 -> dx, which is a string of small latency-bound kernels at B = 12. With
+// `side` != NULL each lin_dw_kernel runs on that stream behind an event recorded when its dy exists, beside the chain;
+// the chain waits for them once per block, before the kernel that overwrites the block's incoming gradient (the last
+// buffer a dW kernel still reads). Event fork/join only: CUDA-graph capturable, results bit-identical.
+static int decoder_train_backward_on(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
+                                     const dfd_decoder_weights* grads, const dfd_kv_taps* taps, const uint8_t* mask,
+                                     int B, int T, int P, const float* d_block_out, float* const* dk, float* const* dv,
+                                     void* saved, size_t saved_bytes, int block_hi, int block_lo, cudaStream_t stream,
+                                     cudaStream_t side, bool* side_forked) {
+  // events 32.. of the context's pool (0..n_blocks-1 belong to the forward's taps)
+  auto dy_ready = [&](int which) -> int {  // the side stream may start the dW kernel of the gradient just produced
+    if (!side) return 0;
+    cudaEvent_t e = ctx->tap_events[32 + which];
+    DFD_CUDA_OK(cudaEventRecord(e, stream));
+    DFD_CUDA_OK(cudaStreamWaitEvent(side, e, 0));
+    *side_forked = true;
+    return 0;
+  };
+  auto join_side = [&]() -> int {
+    if (!side || !*side_forked) return 0;
+    DFD_CUDA_OK(cudaEventRecord(ctx->tap_events[36], side));
+    DFD_CUDA_OK(cudaStreamWaitEvent(stream, ctx->tap_events[36], 0));
+    *side_forked = false;
+    return 0;
+  };
   const TrainBuf tb = train_layout(B, T, D, H, n_blocks);
   DFD_TRY(check_train_args(D, H, n_blocks, w, taps, mask, B, T, P, saved, saved_bytes, tb));
   DFD_CHECK_ARG(grads && d_block_out, "decoder_train_backward: null pointer");
@@ -435,13 +470,15 @@ int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const
       DFD_CUDA_OK(cudaGetLastError());
     }
     // x2 = x1 + c_proj(h): dW_proj, db_proj, dhpre = (dx2 W_proj) * quickgelu'(hpre)
+    DFD_TRY(dy_ready(0));
     DFD_TIMED(DFD_TAG_DEC_LINEAR,
               linear_f32_backward(ctx, h, w->c_proj_weight[i], dx, hpre, nullptr, dh, G(grads->c_proj_weight[i]),
-                                  G(grads->c_proj_bias[i]), B, D, 4 * D, lin, stream));
+                                  G(grads->c_proj_bias[i]), B, D, 4 * D, lin, stream, side));
     // hpre = c_fc(y2): dW_fc, db_fc, dy2
+    DFD_TRY(dy_ready(1));
     DFD_TIMED(DFD_TAG_DEC_LINEAR,
               linear_f32_backward(ctx, y2, w->c_fc_weight[i], dh, nullptr, nullptr, dy, G(grads->c_fc_weight[i]),
-                                  G(grads->c_fc_bias[i]), B, 4 * D, D, lin, stream));
+                                  G(grads->c_fc_bias[i]), B, 4 * D, D, lin, stream, side));
     // y2 = ln_2(x1): dx1 = dx2 + ln_2'(dy2)
     {
       ScopedTimer _t(ctx, DFD_TAG_DEC_OTHER, stream);
@@ -451,9 +488,10 @@ int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const
       DFD_CUDA_OK(cudaGetLastError());
     }
     // x1 = x_in + out_proj(mix): dW_out, db_out, dmix
+    DFD_TRY(dy_ready(2));
     DFD_TIMED(DFD_TAG_DEC_LINEAR,
               linear_f32_backward(ctx, mix, w->out_proj_weight[i], dx1, nullptr, nullptr, dmix,
-                                  G(grads->out_proj_weight[i]), G(grads->out_proj_bias[i]), B, D, D, lin, stream));
+                                  G(grads->out_proj_weight[i]), G(grads->out_proj_bias[i]), B, D, D, lin, stream, side));
     // mix = attention(qs, K_i, V_i): dqs, dpos_emb (summed over the blocks), optionally dK_i / dV_i
     float* dpe = nullptr;
     if (w->positional_embedding) dpe = pe_written ? F(tb.dpe_tmp) : G(grads->positional_embedding);
@@ -470,14 +508,17 @@ int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const
     }
     if (dpe) pe_written = true;
     // qs = in_proj(y1): dW_in, db_in, dy1
+    DFD_TRY(dy_ready(3));
     DFD_TIMED(DFD_TAG_DEC_LINEAR,
               linear_f32_backward(ctx, y1, w->in_proj_weight[i], dqs, nullptr, nullptr, dy, G(grads->in_proj_weight[i]),
-                                  G(grads->in_proj_bias[i]), B, 2 * D, D, lin, stream));
+                                  G(grads->in_proj_bias[i]), B, 2 * D, D, lin, stream, side));
     // y1 = ln_1(x_in): dx_in = dx1 + ln_1'(dy1)
     {
       ScopedTimer _t(ctx, DFD_TAG_DEC_OTHER, stream);
       ln_rows_bwd_param_kernel<<<cblk, cthr, 0, stream>>>(x_in, D, F(bo + tb.st1), dy, G(grads->ln_1_weight[i]),
                                                           G(grads->ln_1_bias[i]), B, D);
+      // dx is about to be overwritten: the block's weight-gradient kernels (c_proj's reads dx) must be done
+      DFD_TRY(join_side());
       ln_rows_bwd_dx_kernel<<<B, 256, 0, stream>>>(x_in, D, w->ln_1_weight[i], F(bo + tb.st1), dy, dx1, dx, D);
       DFD_CUDA_OK(cudaGetLastError());
     }
@@ -495,6 +536,29 @@ int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const
                                                G(grads->class_embedding), D);
   DFD_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+static bool bwd_side_stream_enabled() {  // read per call (a host-side getenv): tests and A/B runs toggle it
+  const char* e = getenv("DFD_BWD_STREAMS");
+  return !(e && e[0] == '0');
+}
+
+int decoder_train_backward(const dfd_ctx* ctx, int D, int H, int n_blocks, const dfd_decoder_weights* w,
+                           const dfd_decoder_weights* grads, const dfd_kv_taps* taps, const uint8_t* mask, int B, int T,
+                           int P, const float* d_block_out, float* const* dk, float* const* dv, void* saved,
+                           size_t saved_bytes, int block_hi, int block_lo, cudaStream_t stream) {
+  // per-kernel timing wants every kernel alone on the device; DFD_BWD_STREAMS=0 keeps everything on `stream`
+  cudaStream_t side = nullptr;
+  if (!ctx->timing && bwd_side_stream_enabled() && ctx->side_stream && ctx->tap_events.size() > 36)
+    side = ctx->side_stream;
+  bool forked = false;
+  const int rc = decoder_train_backward_on(ctx, D, H, n_blocks, w, grads, taps, mask, B, T, P, d_block_out, dk, dv,
+                                           saved, saved_bytes, block_hi, block_lo, stream, side, &forked);
+  if (forked) {  // an error return in the middle of a block: never leave the side stream forked (graph capture)
+    cudaEventRecord(ctx->tap_events[36], side);
+    cudaStreamWaitEvent(stream, ctx->tap_events[36], 0);
+  }
+  return rc;
 }
 
 }  // namespace dfd

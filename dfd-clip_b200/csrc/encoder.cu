@@ -359,45 +359,53 @@ static int ensure_side_stream(const dfd_ctx* ctx, int n_events) {
 // Detector.predict (src/models.py:498-566) as ONE call: the encoder on `stream`, and decoder block i on the
 // context's side stream as soon as the K/V projection of its tapped layer has been enqueued, so that the one-token
 // decoder (launch- and HBM-bound) runs beside the tensor-bound encoder layers that follow the tap. Fork/join with
-// events, so the call is CUDA-graph capturable and `stream` ends up ordered after the whole decoder.
-int predict_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
-                    const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
-                    void* enc_workspace, size_t enc_workspace_bytes, DecoderRun run, const int* tap_layers,
-                    int overlap, cudaStream_t stream) {
-  DFD_CHECK_ARG(tap_layers != nullptr && run.n_blocks > 0, "predict_forward: tap_layers is NULL or no decoder blocks");
-  for (int i = 0; i < run.n_blocks; ++i)
+// events, so the call is CUDA-graph capturable and `stream` ends up ordered after the whole decoder. The decoder is
+// given as three steps (begin / block i / end on a stream): the inference decoder (DecoderRun) for
+// dfd_predict_forward, the activation-saving training forward (DecoderTrainRun) for dfd_train_forward.
+struct DecoderSteps {
+  int n_blocks;
+  std::function<int(cudaStream_t)> begin;
+  std::function<int(int, cudaStream_t)> block;
+  std::function<int(cudaStream_t)> end;
+};
+
+int overlapped_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
+                       const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                       void* enc_workspace, size_t enc_workspace_bytes, const DecoderSteps& dec, const int* tap_layers,
+                       int overlap, cudaStream_t stream, const char* who) {
+  DFD_CHECK_ARG(tap_layers != nullptr && dec.n_blocks > 0, "%s: tap_layers is NULL or no decoder blocks", who);
+  for (int i = 0; i < dec.n_blocks; ++i)
     DFD_CHECK_ARG(tap_layers[i] >= 0 && tap_layers[i] < num_run_layers,
-                  "predict_forward: tap %d is layer %d but only layers [0, %d) run", i, tap_layers[i], num_run_layers);
-  if (n_frames == 0 || run.B == 0) return 0;
+                  "%s: tap %d is layer %d but only layers [0, %d) run", who, i, tap_layers[i], num_run_layers);
   // per-kernel timing wants every kernel alone on the device: no overlap while it is on
   if (!overlap || ctx->timing) {
     DFD_TRY(encoder_forward(ctx, dims, packed, frames, mean_std, n_frames, num_run_layers, last_qkv_only, qkv_out,
                             nullptr, enc_workspace, enc_workspace_bytes, stream));
-    DFD_TRY(run.begin(stream));
-    for (int i = 0; i < run.n_blocks; ++i) DFD_TRY(run.block(i, stream));
-    return run.end(stream);
+    DFD_TRY(dec.begin(stream));
+    for (int i = 0; i < dec.n_blocks; ++i) DFD_TRY(dec.block(i, stream));
+    return dec.end(stream);
   }
-  DFD_TRY(ensure_side_stream(ctx, run.n_blocks));
+  DFD_TRY(ensure_side_stream(ctx, dec.n_blocks));
   cudaStream_t side = ctx->side_stream;
   DFD_CUDA_OK(cudaEventRecord(ctx->fork_event, stream));
   DFD_CUDA_OK(cudaStreamWaitEvent(side, ctx->fork_event, 0));
-  int rc = run.begin(side);
+  int rc = dec.begin(side);
   int next = 0;  // blocks are sequential (block i consumes block i-1's query): issue them in order, each once its
                  // layer (and every earlier block's layer) has been projected
   if (rc == 0)
     rc = encoder_forward(ctx, dims, packed, frames, mean_std, n_frames, num_run_layers, last_qkv_only, qkv_out, nullptr,
                          enc_workspace, enc_workspace_bytes, stream, [&](int layer) -> int {
-                           while (next < run.n_blocks && tap_layers[next] <= layer) {
+                           while (next < dec.n_blocks && tap_layers[next] <= layer) {
                              DFD_CUDA_OK(cudaEventRecord(ctx->tap_events[next], stream));
                              DFD_CUDA_OK(cudaStreamWaitEvent(side, ctx->tap_events[next], 0));
-                             DFD_TRY(run.block(next, side));
+                             DFD_TRY(dec.block(next, side));
                              ++next;
                            }
                            return 0;
                          });
-  if (rc == 0 && next != run.n_blocks)
-    rc = fail(DFD_ERR_INVALID, "predict_forward: %d of %d decoder blocks issued", next, run.n_blocks);
-  if (rc == 0) rc = run.end(side);
+  if (rc == 0 && next != dec.n_blocks) rc = fail(DFD_ERR_INVALID, "%s: %d of %d decoder blocks issued", who, next,
+                                                 dec.n_blocks);
+  if (rc == 0) rc = dec.end(side);
   // always join: a failed call must not leave the side stream forked (a graph capture would be invalidated)
   cudaError_t e1 = cudaEventRecord(ctx->join_event, side);
   cudaError_t e2 = cudaStreamWaitEvent(stream, ctx->join_event, 0);
@@ -405,6 +413,32 @@ int predict_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pa
   DFD_CUDA_OK(e1);
   DFD_CUDA_OK(e2);
   return 0;
+}
+
+int predict_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
+                    const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                    void* enc_workspace, size_t enc_workspace_bytes, DecoderRun run, const int* tap_layers,
+                    int overlap, cudaStream_t stream) {
+  if (n_frames == 0 || run.B == 0) return 0;
+  const DecoderSteps steps{run.n_blocks, [&](cudaStream_t s) { return run.begin(s); },
+                           [&](int i, cudaStream_t s) { return run.block(i, s); },
+                           [&](cudaStream_t s) { return run.end(s); }};
+  return overlapped_forward(ctx, dims, packed, frames, mean_std, n_frames, num_run_layers, last_qkv_only, qkv_out,
+                            enc_workspace, enc_workspace_bytes, steps, tap_layers, overlap, stream, "predict_forward");
+}
+
+// The forward half of the trainer's step (src/trainer.py:147-156: frozen encoder, then the decoder under autograd) as
+// ONE call: like predict_forward, with the activation-saving decoder forward of decoder_train.cu on the side stream.
+int train_forward(const dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames,
+                  const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                  void* enc_workspace, size_t enc_workspace_bytes, DecoderTrainRun run, const int* tap_layers,
+                  int overlap, cudaStream_t stream) {
+  DFD_CHECK_ARG(n_frames > 0 && run.B > 0, "train_forward: empty batch");
+  const DecoderSteps steps{run.n_blocks, [&](cudaStream_t s) { return run.begin(s); },
+                           [&](int i, cudaStream_t s) { return run.block(i, s); },
+                           [](cudaStream_t) { return 0; }};
+  return overlapped_forward(ctx, dims, packed, frames, mean_std, n_frames, num_run_layers, last_qkv_only, qkv_out,
+                            enc_workspace, enc_workspace_bytes, steps, tap_layers, overlap, stream, "train_forward");
 }
 
 }  // namespace dfd
@@ -427,6 +461,23 @@ int dfd_predict_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* pack
   return dfd::predict_forward(ctx, dims, packed, frames, frames_are_u8 ? mean_std : nullptr, n_frames, num_run_layers,
                               last_qkv_only, qkv_out, enc_workspace, enc_workspace_bytes, run, tap_layers, overlap,
                               static_cast<cudaStream_t>(stream));
+}
+
+int dfd_train_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames, int frames_are_u8,
+                      const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                      void* enc_workspace, size_t enc_workspace_bytes, int D, int H, int n_blocks,
+                      const dfd_decoder_weights* w, const dfd_kv_taps* taps, const int* tap_layers, const uint8_t* mask,
+                      int B, int T, int P, float* block_out, void* saved, size_t saved_bytes, int overlap,
+                      void* stream) {
+  dfd::clear_error();
+  if (!ctx) return dfd::fail(DFD_ERR_INVALID, "dfd_train_forward: ctx is NULL");
+  if (frames_are_u8 && !mean_std) return dfd::fail(DFD_ERR_INVALID, "dfd_train_forward: mean_std is NULL");
+  if (static_cast<int64_t>(B) * T != n_frames)
+    return dfd::fail(DFD_ERR_INVALID, "dfd_train_forward: %d clips x %d frames != %d frames", B, T, n_frames);
+  dfd::DecoderTrainRun run{ctx, D, H, n_blocks, w, taps, mask, B, T, P, block_out, saved, saved_bytes};
+  return dfd::train_forward(ctx, dims, packed, frames, frames_are_u8 ? mean_std : nullptr, n_frames, num_run_layers,
+                            last_qkv_only, qkv_out, enc_workspace, enc_workspace_bytes, run, tap_layers, overlap,
+                            static_cast<cudaStream_t>(stream));
 }
 
 size_t dfd_encoder_packed_bytes(const dfd_vit_dims* dims) {

@@ -100,6 +100,22 @@ struct DecoderRun {
   int end(cudaStream_t stream);
 };
 
+// The activation-saving decoder forward of the training step (decoder_train.cu) in the same steps; dfd_train_forward
+// issues block i on the side stream behind its tap, dfd_decoder_train_forward runs them back to back.
+struct DecoderTrainRun {
+  const dfd_ctx* ctx;
+  int D, H, n_blocks;
+  const dfd_decoder_weights* w;
+  const dfd_kv_taps* taps;
+  const uint8_t* mask;
+  int B, T, P;
+  float* block_out;
+  void* saved;
+  size_t saved_bytes;
+  int begin(cudaStream_t stream);
+  int block(int i, cudaStream_t stream);
+};
+
 // Thread-local last-error string (dfd_last_error). Returns `code` so callers can `return fail(...)`.
 int fail(int code, const char* fmt, ...);
 void clear_error();

@@ -189,17 +189,30 @@ class _DecoderChainFn(torch.autograd.Function):
     the decoder holds a ``_grad_sink`` (``training.TrainStep``) — straight into the caller's flat gradient buffer."""
 
     @staticmethod
-    def forward(ctx, decoder, kvs, m, *params):
+    def forward(ctx, decoder, kvs, m, enc, *params):
         plan = decoder._run_plan(kvs, m)
         lib, dev = _native.load_library(), plan["dev"]
         d, h, nb, b, t, p = decoder.width, decoder.heads, plan["nb"], plan["b"], plan["t"], plan["p"]
         nbytes = lib.dfd_decoder_train_bytes(b, t, d, nb)
         saved = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _native.check(lib.dfd_decoder_train_forward(
-                _native.ctx(dev), d, h, nb, ctypes.byref(plan["w"]), ctypes.byref(plan["taps"]),
-                _native.ptr(plan["mask"]), b, t, p, _native.ptr(plan["block_out"]), _native.ptr(saved), nbytes,
-                _native.stream_ptr(dev)))
+            if enc is None:
+                _native.check(lib.dfd_decoder_train_forward(
+                    _native.ctx(dev), d, h, nb, ctypes.byref(plan["w"]), ctypes.byref(plan["taps"]),
+                    _native.ptr(plan["mask"]), b, t, p, _native.ptr(plan["block_out"]), _native.ptr(saved), nbytes,
+                    _native.stream_ptr(dev)))
+            else:
+                # the taps are not computed yet: `kvs` are views of the encoder plan's (empty) QKV buffers, and ONE
+                # native call runs the frozen encoder with decoder block i right behind the projection of its tap
+                ep, tap_layers = enc
+                if plan["copied"]:
+                    raise _native.NativeError("single-call training forward needs the decoder to read the taps in place")
+                _native.check(lib.dfd_train_forward(
+                    _native.ctx(dev), ctypes.byref(ep["dims"]), _native.ptr(ep["packed"]), _native.ptr(ep["x"]),
+                    1 if ep["x"].dtype == torch.uint8 else 0, ep["mean_std"], ep["n"], ep["run_layers"], ep["qkv_only"],
+                    ep["qkv_pp"], _native.ptr(ep["ws"]), ep["ws_bytes"], d, h, nb, ctypes.byref(plan["w"]),
+                    ctypes.byref(plan["taps"]), tap_layers, _native.ptr(plan["mask"]), b, t, p,
+                    _native.ptr(plan["block_out"]), _native.ptr(saved), nbytes, 1, _native.stream_ptr(dev)))
         # keep what the backward needs, but NOT the output tensor: ctx -> block_out -> grad_fn -> ctx would be a
         # reference cycle that keeps the whole graph (and the parameters' AccumulateGrad nodes, with the stream they
         # were created on) alive until the garbage collector runs
@@ -239,7 +252,7 @@ class _DecoderChainFn(torch.autograd.Function):
                 if hook is not None:
                     hook(hi)
         del keep
-        return (None, None, None) + tuple(returned)
+        return (None, None, None, None) + tuple(returned)
 
 
 class Decoder(nn.Module):
@@ -357,7 +370,14 @@ class Decoder(nn.Module):
         Returns ``(task_logits, video_feature)`` like the reference (:323-361); logits are NOT yet normalised."""
         return self.run(kvs, m, logit_scale=0.0)
 
-    def run_autograd(self, kvs, m, logit_scale=0.0):
+    def native_chain_ok(self, kvs=None):
+        """True when the whole one-token chain can run as the native autograd node (``_DecoderChainFn``): frozen taps,
+        no ``op_mode.attn_mode``, no active dropout (``DFD_NATIVE_DECODER_BWD=0`` forces the torch-module path)."""
+        kv_grad = kvs is not None and any(kv[n].requires_grad for kv in kvs for n in ("k", "v"))
+        return not kv_grad and not self.attn_mode and not (self.training and self.dropout > 0) and \
+            os.environ.get("DFD_NATIVE_DECODER_BWD", "1") != "0"
+
+    def run_autograd(self, kvs, m, logit_scale=0.0, enc=None):
         """Differentiable ``run`` for the training step (reference :568-596 with ``train=True``). Default: the whole
         one-token chain is ONE autograd node with native forward and hand-written native backward
         (``_DecoderChainFn``), the tail (ln_post, projections, normalisation) a few torch ops on ``[B, D]``. With a
@@ -369,13 +389,14 @@ class Decoder(nn.Module):
         h, d = self.heads, self.width
         if k0.device.type != "cuda":
             raise _native.NativeError("dfdclip_b200 decoder needs CUDA tensors (no CPU fallback)")
-        kv_grad = any(kv[n].requires_grad for kv in kvs for n in ("k", "v"))
-        if not kv_grad and not self.attn_mode and not (self.training and self.dropout > 0) and \
-                os.environ.get("DFD_NATIVE_DECODER_BWD", "1") != "0":
-            # frozen taps, no active dropout: the whole chain is one native forward / backward node
-            stack = _DecoderChainFn.apply(self, kvs, m, *self._chain_params())
+        if self.native_chain_ok(kvs):
+            # frozen taps, no active dropout: the whole chain is one native forward / backward node (with `enc`, the
+            # frozen encoder runs inside the same native call, see Detector._train_single_call)
+            stack = _DecoderChainFn.apply(self, kvs, m, enc, *self._chain_params())
             outs = list(stack.unbind(dim=1))
         else:
+            if enc is not None:
+                raise _native.NativeError("the single-call training forward needs the native decoder chain")
             # trainable adapter on the taps (dK / dV needed), op_mode.attn_mode or active dropout: torch modules around
             # the attention
             x = self.drop_pre(self.ln_pre(self.class_embedding.view(1, d)).expand(b, d))
@@ -783,6 +804,8 @@ class Detector(nn.Module):
         b, t = x.shape[:2]
         if self._single_call_ok(train) and b > 0:
             return self._predict_single_call(x, m, with_video_features)
+        if self._train_single_call_ok(train) and b > 0 and not with_adapt_features:
+            return self._train_single_call(x, m, with_video_features)
         with torch.no_grad():
             qkv, _ = self.encoder.encode(x.flatten(0, 1), keep_layers=self.layer_indices)
         return self.predict_from_taps(qkv, m, b, t, with_video_features=with_video_features,
@@ -799,6 +822,28 @@ class Detector(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()):
             return False
         return not (self.decoder.training and self.decoder.dropout > 0)
+
+    def _train_single_call_ok(self, train):
+        """The training step's forward (frozen encoder, decoder under autograd; reference ``src/trainer.py:147-156``)
+        goes through ``dfd_train_forward`` — encoder and activation-saving decoder forward in one native call, decoder
+        block i beside the encoder layers after its tap — whenever the native decoder chain applies: no adapter, no
+        patch gather, no ``attn_mode``, no active dropout. ``DFD_OVERLAP=0`` keeps the two calls."""
+        if self.adapter is not None or os.environ.get("DFD_OVERLAP", "1") == "0":
+            return False
+        if train and "patch_mask" in self.train_mode:
+            return False
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters())):
+            return False
+        return self.decoder.native_chain_ok()
+
+    def _train_single_call(self, x, m, with_video_features=False):
+        b, t = x.shape[:2]
+        with torch.no_grad():
+            ep = self.encoder._encode_plan(x.flatten(0, 1), keep_layers=self.layer_indices)
+            kvs = self.taps_from_qkv(ep["qkv"], b, t)
+        tap_layers = (ctypes.c_int * len(self.layer_indices))(*self.layer_indices)
+        task_logits, video_features = self.decoder.run_autograd(kvs, m, logit_scale=5.0, enc=(ep, tap_layers))
+        return task_logits, ({"video": video_features} if with_video_features else {})
 
     def _predict_single_call(self, x, m, with_video_features=False):
         b, t = x.shape[:2]

@@ -283,6 +283,19 @@ class TrainStep:
                 self.graph.replay()
             yield self.loss, self.logits
 
+    def close(self):
+        """Release the captured graph and unhook from the detector. On several GPUs call this BEFORE
+        ``torch.distributed.destroy_process_group()``: NCCL keeps the plans of captured collectives alive until their
+        graph is destroyed, and tearing the communicator down first waits for that forever."""
+        import gc
+        torch.cuda.synchronize(self.dev)
+        self.graph = None
+        self.loss = self.logits = None
+        self.det.decoder._block_grad_hook = None   # bound method: detector -> step -> detector cycle otherwise
+        self.det.decoder._grad_sink = None
+        gc.collect()
+        torch.cuda.synchronize(self.dev)
+
     def eager(self, x, y, m, speed=None):
         """The same step without the graph (per-kernel timing, debugging)."""
         self._load(x, y, m, speed)

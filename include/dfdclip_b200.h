@@ -372,6 +372,18 @@ int dfd_decoder_train_backward(dfd_ctx* ctx, int D, int H, int n_blocks, const d
                                int T, int P, const float* d_block_out, float* const* dk, float* const* dv, void* saved,
                                size_t saved_bytes, int block_hi, int block_lo, void* stream);
 
+/* The forward half of the trainer's step (src/trainer.py:147-156: frozen encoder under no_grad, then the decoder) as
+ * ONE call = dfd_encoder_forward[_u8] + dfd_decoder_train_forward with the same arguments; with overlap != 0 the
+ * activation-saving decoder block i runs on the context's stream right behind the K/V projection of encoder layer
+ * tap_layers[i], beside the encoder layers that follow (same fork/join as dfd_predict_forward: graph capturable,
+ * bit-identical to the two separate calls). The backward is dfd_decoder_train_backward on the same `saved`. */
+int dfd_train_forward(dfd_ctx* ctx, const dfd_vit_dims* dims, const void* packed, const void* frames, int frames_are_u8,
+                      const float* mean_std, int n_frames, int num_run_layers, int last_qkv_only, void* const* qkv_out,
+                      void* enc_workspace, size_t enc_workspace_bytes, int D, int H, int n_blocks,
+                      const dfd_decoder_weights* w, const dfd_kv_taps* taps, const int* tap_layers, const uint8_t* mask,
+                      int B, int T, int P, float* block_out, void* saved, size_t saved_bytes, int overlap,
+                      void* stream);
+
 /* Backward of one of the decoder's nn.Linear layers (dfd_linear_f32), exported for unit tests:
  * dx[b,k] = (sum_n dy[b,n] W[n,k]) * quickgelu'(gelu_pre[b,k]) + dx_add[b,k];  dW[n,k] = sum_b dy[b,n] x[b,k];
  * db[n] = sum_b dy[b,n]. gelu_pre / dx_add / dx / dW / db may be NULL (db is only written together with dW). */

@@ -381,6 +381,39 @@ def test_native_decoder_chain_backward_matches_the_torch_module_path(cuda_device
         assert err < 2e-4 * scale + 1e-7, (name, err, scale)
 
 
+@pytest.mark.parametrize("op_mode", [None, {"global_prediction": 1, "aug_query": 1}])
+def test_single_call_training_forward_is_bit_identical_to_two_calls(cuda_device, monkeypatch, op_mode):
+    """dfd_train_forward (encoder with the activation-saving decoder blocks on the side stream behind their taps)
+    against dfd_encoder_forward + dfd_decoder_train_forward (DFD_OVERLAP=0): same kernels on the same data, so loss,
+    logits and every gradient are bit-identical — also for uint8 frames. The second setting also moves the backward's
+    weight-gradient kernels onto the side stream (DFD_BWD_STREAMS)."""
+    from dfdclip_b200 import synthetic
+    det, _ = _build_small_detector(cuda_device, op_mode)
+    x, m = synthetic.make_clips(5, 3, 64, seed=33)
+    y = torch.tensor([1, 0, 1, 0, 0], device=cuda_device)
+    mean = torch.tensor(det.encoder.input_mean).view(1, 1, 3, 1, 1)
+    std = torch.tensor(det.encoder.input_std).view(1, 1, 3, 1, 1)
+    x_u8 = ((x * std + mean).clamp(0, 1) * 255).round().to(torch.uint8)
+    for frames in (x, x_u8):
+        results = []
+        for overlap in ("0", "1"):
+            monkeypatch.setenv("DFD_OVERLAP", overlap)
+            monkeypatch.setenv("DFD_BWD_STREAMS", overlap)  # weight gradients beside the dx chain of the backward
+            det.zero_grad(set_to_none=True)
+            with torch.enable_grad():
+                assert det._train_single_call_ok(True) == (overlap == "1")
+                losses, logits, _ = det(frames.to(cuda_device), [y], m.to(cuda_device), train=True, single_task=0)
+                losses[0].mean().backward()
+            torch.cuda.synchronize()
+            results.append((losses[0].detach().clone(), logits[0].detach().clone(),
+                            {n: p.grad.detach().clone() for n, p in det.named_parameters() if p.requires_grad}))
+        (l0, g0, gr0), (l1, g1, gr1) = results
+        assert torch.equal(l0, l1) and torch.equal(g0, g1)
+        assert set(gr0) == set(gr1) and len(gr1) >= 40
+        for name in gr0:
+            assert torch.equal(gr0[name], gr1[name]), name
+
+
 @pytest.mark.parametrize("mode", ["frame", "temporal+frame"])
 def test_training_step_with_attn_mode_matches_oracle(cuda_device, mode):
     """op_mode.attn_mode in the training step (the shipped deepfake configs train with it): loss and decoder gradients

@@ -5,7 +5,7 @@ N=${1:-2}; shift
 WL=${@:-c2 c3 c5 c4}
 for w in $WL; do
   case $w in c2) A="--steps 20 --warmup 3";; c3) A="--workload c3 --steps 2 --warmup 1";; c5) A="--workload c5 --steps 30 --warmup 5";; c4) A="--workload c4 --steps 10 --warmup 3";; esac
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $N $A > gpurun_out/r2_bench_${w}_n$N.json 2> gpurun_out/r2_bench_${w}_n$N.err
+  timeout ${SCALE_TIMEOUT:-240} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $N $A > gpurun_out/r2_bench_${w}_n$N.json 2> gpurun_out/r2_bench_${w}_n$N.err
   echo "$w n$N rc=$?"; tail -2 gpurun_out/r2_bench_${w}_n$N.err | cut -c1-200
 done
 python - "$N" <<'PY'
