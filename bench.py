@@ -680,7 +680,7 @@ def run_c5(args, rank, world, local_rank):
     y_host = torch.randint(0, 2, (clips,), generator=g).pin_memory()
     m_host = torch.ones((clips, frames), dtype=torch.bool).pin_memory()
     x, y, m = x_host.to(dev), y_host.to(dev), m_host.to(dev)
-    step = TrainStep(det, opt, x, y, m, group=(dist.group.WORLD if dist else None))
+    step = TrainStep(det, opt, x, y, m, group=(dist.group.WORLD if dist else None), pipeline=bool(args.c5_pipeline))
 
     for _ in range(max(args.warmup, 3)):
         step(x, y, m)
@@ -724,7 +724,7 @@ def run_c5(args, rank, world, local_rank):
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         same = bool((lo == hi).item())
     # roofline of the encoder GEMMs inside the step: an eager (un-graphed) pass of the same step with launch events
-    kernel_ms = timed_kernels(dev, lambda: step.eager(x, y, m), 3)
+    kernel_ms = timed_kernels(dev, lambda: step.eager(x, y, m, serial=True), 3)
     description, launches = step.describe(), step.launches_per_step
     step.close()   # the graph holds captured NCCL plans: it must go before the process group does
     if rank != 0:
@@ -794,6 +794,8 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=None, help="clips per step of the CPU reference arm / "
                     "cpu_baseline sample (default: 16 = the reference's own chunk size, scripts/inference.sh; 2 for "
                     "ViT-L/14 x 16 frames, 4 for the training step)")
+    ap.add_argument("--c5-pipeline", type=int, default=0, choices=[0, 1],
+                    help="c5: TrainStep(pipeline=...): encode batch k+1 beside the decoder step of batch k")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap-decoder", action="store_true",
                     help="e2e stream: run the decoder on the encoder's stream instead of beside the next batch's encoder")

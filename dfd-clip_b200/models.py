@@ -930,8 +930,12 @@ class Detector(nn.Module):
             masked.append({name: t.index_select(2, idx) for name, t in kv.items()})
         return masked
 
-    def forward(self, x, y, m, comp=None, speed=None, train=False, single_task=None, *args, **kargs):
-        """Eval: ``(task_losses, task_logits)``; train adds ``other_losses`` (reference :568-596, 738)."""
+    def forward(self, x, y, m, comp=None, speed=None, train=False, single_task=None, *args, taps=None, **kargs):
+        """Eval: ``(task_losses, task_logits)``; train adds ``other_losses`` (reference :568-596, 738).
+
+        ``taps`` (not in the reference): the packed per-layer QKV buffers of an ``encoder.encode(...)`` call already
+        made for these clips (``x`` is then only consulted for its batch shape): the frozen encoder does not depend on
+        the optimizer, so a trainer may encode batch k+1 while batch k trains (``training.TrainStep(pipeline=True)``)."""
         if "ema_frame" in self.op_mode and self.op_mode.ema_frame:
             # exponential moving average over the frames -> one frame per clip (reference :572-578)
             if x.dtype == torch.uint8:
@@ -939,7 +943,13 @@ class Detector(nn.Module):
             x = _native.ema_frames(x, float(self.op_mode.ema_frame))
             m = m[:, 0].unsqueeze(1)
         b = x.shape[0]
-        task_logits, features = self.predict(x, m, with_video_features=True, train=train)
+        if taps is None:
+            task_logits, features = self.predict(x, m, with_video_features=True, train=train)
+        else:
+            if "ema_frame" in self.op_mode and self.op_mode.ema_frame:
+                raise NotImplementedError("taps= and op_mode.ema_frame: encode the averaged frames yourself")
+            task_logits, features = self.predict_from_taps(taps, m, b, m.shape[1], with_video_features=True,
+                                                           train=train)
         video_features = features["video"]
         task_losses = [
             loss_fn(logits, labels) if single_task is None or i == single_task else 0

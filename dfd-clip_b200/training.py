@@ -32,12 +32,20 @@ class TrainStep:
       (``OneCycleLR(cycle_momentum=True)``) cannot be replayed and raises.
     * ``loss`` (scalar: mean task loss + auxiliary losses) and ``logits`` are views of static buffers that the next call
       overwrites.
+    * ``pipeline=True``: the encoder is frozen, so its forward on batch k+1 does not depend on the optimizer step of
+      batch k. The step then runs as a two-stage pipeline ACROSS calls: call k trains the decoder on batch k-1 (taps
+      encoded by the previous call) while a second stream encodes batch k into the other of two tap buffers — the
+      launch-bound decoder forward / backward / all-reduce / SGD hides under the tensor-bound encoder. ``step(x, y, m)``
+      returns the loss / logits of the PREVIOUS batch (``(None, None)`` on the first call, which only encodes);
+      ``step.flush()`` trains the last batch. The parameters after ``flush()`` equal those of the un-pipelined step on the
+      same batches (every batch sees the same weights as in the reference's loop).
     * Not capturable (raise up front): ``train_mode.patch_mask`` (patch indices drawn on the host with numpy per step,
       reference :511-544), ``train_mode.temporal`` (host-side argsort / shuffle, :676-736) and class-weighted losses
       (a host list turned into a tensor inside the loss, :36-37). Use ``graph=False`` (eager body, same arithmetic).
     """
 
-    def __init__(self, detector, optimizer, x, y, m, single_task=0, speed=None, group=None, warmup=2, graph=True):
+    def __init__(self, detector, optimizer, x, y, m, single_task=0, speed=None, group=None, warmup=2, graph=True,
+                 pipeline=False):
         dev = x.device
         if dev.type != "cuda":
             raise RuntimeError("TrainStep needs CUDA tensors (dfdclip_b200 has no CPU path)")
@@ -60,6 +68,20 @@ class TrainStep:
             self.world = dist.get_world_size(group)
         self.x, self.y, self.m = x.clone(), y.clone(), m.clone()
         self.speed = None if speed is None else speed.clone()
+        self.pipeline = bool(pipeline)
+        if self.pipeline:
+            if detector.adapter is not None or speed is not None or "patch_mask" in detector.train_mode or \
+                    ("ema_frame" in detector.op_mode and detector.op_mode.ema_frame):
+                raise NotImplementedError("TrainStep(pipeline=True) covers the frozen-encoder step without adapter, "
+                                          "patch_mask, ema_frame or auxiliary speed losses")
+            enc = detector.encoder
+            rows = x.shape[0] * x.shape[1] * enc.tokens_per_frame
+            # two input slots and two sets of tap buffers: a call trains on one while the encoder fills the other
+            self._slots = [(self.x, self.y, self.m), (x.clone(), y.clone(), m.clone())]
+            self._taps = [{l: torch.empty((rows, 3 * enc.width), dtype=torch.bfloat16, device=dev)
+                           for l in detector.layer_indices} for _ in range(2)]
+            self._enc_stream = torch.cuda.Stream(dev)
+            self._cur, self._primed = 0, False    # slot the next call trains on; whether its taps exist
         self.params = [p for g in optimizer.param_groups for p in g["params"]]
         self._build_flat_gradients()
         # lr as a device tensor: the captured fused-SGD kernel reads it at replay time
@@ -76,16 +98,24 @@ class TrainStep:
         self.launches_per_step = (4 + 7 * max(taps) + 2) + (1 + 12 * nb) + (19 * nb + 2 * (nb - 1) + 3)
         self.graph = None
         # warm-up and capture run on ONE side stream: autograd runs a parameter's gradient accumulation on the stream
-        # that was current when its accumulator node was created, which must be the capturing stream
-        self._side = torch.cuda.Stream(dev)
+        # that was current when its accumulator node was created, which must be the capturing stream. Pipelined, that
+        # stream carries the decoder's small kernels beside the encoder's: high priority, so that they are placed as
+        # soon as an SM frees up
+        self._side = torch.cuda.Stream(dev, priority=-1) if self.pipeline else torch.cuda.Stream(dev)
         self._warm_up(max(1, int(warmup)))
         if graph:
             import gc
             gc.collect()  # no autograd graph of the warm-up may survive into the capture
-            self.graph = torch.cuda.CUDAGraph()
             # thread_local: other threads (NVML sampling, NCCL's watchdog) may touch CUDA while this one captures
-            with torch.cuda.graph(self.graph, stream=self._side, capture_error_mode="thread_local"):
-                self.loss, self.logits = self._body()
+            self._graphs, self._outs = [], []
+            for slot in ((0, 1) if self.pipeline else (0,)):   # pipelined: one graph per (train slot, encode slot)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._side, capture_error_mode="thread_local"):
+                    out = self._body(slot)
+                self._graphs.append(g)
+                self._outs.append(out)
+            self.graph = self._graphs[0]
+            self.loss, self.logits = self._outs[0]
 
     # ------------------------------------------------------------------------------------------ set-up
     @staticmethod
@@ -158,8 +188,11 @@ class TrainStep:
         side = self._side
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
-            for _ in range(n):
-                self._body()
+            if self.pipeline:   # both tap buffers hold the example batch's taps during warm-up and capture
+                self._encode(0)
+                self._encode(1)
+            for i in range(n):
+                self._body(i % 2 if self.pipeline else 0)
             # undo the warm-up: parameters and buffers back, optimizer state as freshly created
             with torch.no_grad():
                 for p, s in zip(self.params, saved):
@@ -174,12 +207,27 @@ class TrainStep:
         torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------------------------------ the step
-    def _body(self):
+    def _encode(self, slot):
+        """Frozen encoder on the clips of input slot `slot` into its tap buffers (current stream)."""
+        with torch.no_grad():
+            self.det.encoder.encode(self._slots[slot][0].flatten(0, 1), keep_layers=self.det.layer_indices,
+                                    qkv_into=self._taps[slot])
+
+    def _body(self, slot=0):
+        """One step. Pipelined: train on input slot `slot` (taps already there) while the encoder stream fills the
+        other slot's tap buffers from its clips; the two meet again at the end of the step."""
+        x, y, m, taps = self.x, self.y, self.m, None
+        if self.pipeline:
+            main = torch.cuda.current_stream(self.dev)
+            self._enc_stream.wait_stream(main)
+            with torch.cuda.stream(self._enc_stream):
+                self._encode(1 - slot)
+            (x, y, m), taps = self._slots[slot], self._taps[slot]
         with torch.enable_grad():
             for p in self._tail:          # autograd ACCUMULATES into existing .grad tensors
                 p.grad.zero_()
-            losses, logits, other = self.det(self.x, [self.y] * (self.task + 1), self.m, speed=self.speed, train=True,
-                                             single_task=self.task)
+            losses, logits, other = self.det(x, [y] * (self.task + 1), m, speed=self.speed, train=True,
+                                             single_task=self.task, taps=taps)
             loss = losses[self.task].mean()
             for v in other.values():
                 loss = loss + v
@@ -197,16 +245,19 @@ class TrainStep:
                         self.dist.all_reduce(self.flat[lo:hi], op=self.dist.ReduceOp.AVG, group=self.group)
                 main.wait_stream(self._comm)
         self.opt.step()
+        if self.pipeline:
+            torch.cuda.current_stream(self.dev).wait_stream(self._enc_stream)
         return loss.detach(), logits[self.task].detach()
 
-    def _load(self, x, y, m, speed):
+    def _load(self, x, y, m, speed, slot=0):
         if x.shape != self.x.shape or x.dtype != self.x.dtype or y.shape != self.y.shape or m.shape != self.m.shape:
             raise ValueError("batch %s/%s/%s does not match the captured step %s/%s/%s" % (
                 tuple(x.shape), tuple(y.shape), tuple(m.shape), tuple(self.x.shape), tuple(self.y.shape),
                 tuple(self.m.shape)))
-        self.x.copy_(x, non_blocking=True)
-        self.y.copy_(y, non_blocking=True)
-        self.m.copy_(m, non_blocking=True)
+        sx, sy, sm = self._slots[slot] if self.pipeline else (self.x, self.y, self.m)
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        sm.copy_(m, non_blocking=True)
         if self.speed is not None:
             if speed is None:
                 raise ValueError("the captured step takes a `speed` tensor")
@@ -228,13 +279,48 @@ class TrainStep:
         """After ``scheduler.step()``: copy the scheduler's current learning rates into the captured step."""
         self.set_lr([float(v) for v in scheduler.get_last_lr()])
 
-    def __call__(self, x, y, m, speed=None):
-        self._load(x, y, m, speed)
+    def _run(self, slot=0):
         if self.graph is None:
-            self.loss, self.logits = self._body()
+            self.loss, self.logits = self._body(slot)
         else:
-            self.graph.replay()
+            self._graphs[slot].replay()
+            self.loss, self.logits = self._outs[slot]
         return self.loss, self.logits
+
+    def _push(self, x, y, m, speed=None, loaded=None):
+        """One call of the step on device tensors; `loaded()` is called once the batch has been copied into the step's
+        static buffers (the caller's tensors are free again). Pipelined: returns the result of the PREVIOUS batch, None
+        for the first batch (which is only encoded)."""
+        loaded = loaded or (lambda: None)
+        if not self.pipeline:
+            self._load(x, y, m, speed)
+            loaded()
+            return self._run()
+        if not self._primed:
+            self._load(x, y, m, speed, slot=self._cur)
+            loaded()
+            self._encode(self._cur)
+            self._primed = True
+            return None
+        cur = self._cur
+        self._load(x, y, m, speed, slot=1 - cur)
+        loaded()
+        out = self._run(cur)
+        self._cur = 1 - cur
+        return out
+
+    def __call__(self, x, y, m, speed=None):
+        out = self._push(x, y, m, speed)
+        return (None, None) if out is None else out
+
+    def flush(self):
+        """Pipelined step: train the last batch handed in (its successor's encoder pass runs on stale clips and is
+        discarded). Returns that batch's ``(loss, logits)``, or ``(None, None)`` if nothing is pending."""
+        if not self.pipeline or not self._primed:
+            return None, None
+        out = self._run(self._cur)
+        self._primed = False
+        return out
 
     def run_host(self, batches):
         """The trainer loop over HOST batches (the reference's DataLoader hands out CPU tensors that the Accelerate-
@@ -273,15 +359,17 @@ class TrainStep:
             except StopIteration:
                 nxt = None
             main.wait_event(ev)
-            self._load(*self._staging[slot], None if self.speed is None else self.speed)
-            free = torch.cuda.Event()
-            free.record(main)
-            self._staged_free[slot] = free
-            if self.graph is None:
-                self.loss, self.logits = self._body()
-            else:
-                self.graph.replay()
-            yield self.loss, self.logits
+
+            def release(slot=slot):   # the staged batch is in the step's static buffers: the copy stream may refill it
+                free = torch.cuda.Event()
+                free.record(main)
+                self._staged_free[slot] = free
+
+            out = self._push(*self._staging[slot], None if self.speed is None else self.speed, loaded=release)
+            if out is not None:
+                yield out
+        if self.pipeline and self._primed:
+            yield self.flush()
 
     def close(self):
         """Release the captured graph and unhook from the detector. On several GPUs call this BEFORE
@@ -290,16 +378,29 @@ class TrainStep:
         import gc
         torch.cuda.synchronize(self.dev)
         self.graph = None
+        self._graphs, self._outs = [], []
         self.loss = self.logits = None
         self.det.decoder._block_grad_hook = None   # bound method: detector -> step -> detector cycle otherwise
         self.det.decoder._grad_sink = None
         gc.collect()
         torch.cuda.synchronize(self.dev)
 
-    def eager(self, x, y, m, speed=None):
-        """The same step without the graph (per-kernel timing, debugging)."""
-        self._load(x, y, m, speed)
-        return self._body()
+    def eager(self, x, y, m, speed=None, serial=False):
+        """The same step without the graph (per-kernel timing, debugging). Pipelined: trains on the pending batch (the
+        example batch if none) and encodes this one; ``serial=True`` runs the un-pipelined body instead (encoder, then
+        decoder, on one stream: what per-kernel timing needs)."""
+        if not self.pipeline or serial:
+            was, self.pipeline = self.pipeline, False
+            try:
+                self._load(x, y, m, speed)
+                return self._body()
+            finally:
+                self.pipeline = was
+        cur = self._cur
+        self._load(x, y, m, speed, slot=1 - cur)
+        out = self._body(cur)
+        self._cur, self._primed = 1 - cur, True
+        return out
 
     def describe(self):
         return ("Detector.forward(train=True) + backward + %sfused SGD, %s; native encoder, native decoder chain "
@@ -307,7 +408,9 @@ class TrainStep:
                     "all_reduce(AVG) over %d ranks (%s) + " % (
                         self.world, "per decoder block, overlapped with the backward" if self._block_slices
                         else "one call") if self.world > 1 else "",
-                    "one CUDA graph replay per step" if self.graph is not None else "eager"))
+                    ("one CUDA graph replay per step" if self.graph is not None else "eager") +
+                    ("; two-stage pipeline across steps: the encoder of batch k+1 runs beside the decoder forward / "
+                     "backward / optimizer step of batch k" if self.pipeline else "")))
 
 
 class GraphedTrainStep(TrainStep):

@@ -304,6 +304,60 @@ def test_graphed_train_step_matches_eager_steps(cuda_device, u8):
         step(batches[0][0][:2], batches[0][1][:2], batches[0][2][:2])
 
 
+@pytest.mark.parametrize("graph", [True, False])
+def test_pipelined_train_step_matches_the_plain_step(cuda_device, graph):
+    """TrainStep(pipeline=True) — the frozen encoder of batch k+1 beside the decoder step of batch k — against the plain
+    TrainStep on the same five batches: the loss / logits of batch k come back one call later and are identical, the
+    first call returns nothing, flush() trains the last batch, and the trained parameters end up bit-identical; also
+    through run_host from pinned batches."""
+    import copy
+    from dfdclip_b200 import synthetic
+    from dfdclip_b200.training import TrainStep
+    det_a, _ = _build_small_detector(cuda_device)
+    det_b = copy.deepcopy(det_a)
+    res = 64
+    batches = []
+    for i in range(5):
+        x, m = synthetic.make_clips(4, 3, res, seed=90 + i)
+        if i == 3:
+            m[1, -1] = False
+        y = torch.randint(0, 2, (4,), generator=torch.Generator().manual_seed(40 + i))
+        batches.append((x, y, m))
+    dev_batches = [tuple(t.to(cuda_device) for t in b) for b in batches]
+
+    plain = TrainStep(det_a, det_a.configure_optimizers(lr=0.05), *dev_batches[0], graph=graph)
+    ref = []
+    for b in dev_batches:
+        loss, logits = plain(*b)
+        ref.append((loss.clone(), logits.clone()))
+
+    before = [p.detach().clone() for p in det_b.parameters()]
+    piped = TrainStep(det_b, det_b.configure_optimizers(lr=0.05), *dev_batches[4], graph=graph, pipeline=True)
+    torch.cuda.synchronize()
+    assert all(torch.equal(p, q) for p, q in zip(det_b.parameters(), before))   # constructing it does not train
+    got = []
+    for k, b in enumerate(dev_batches[:3]):
+        loss, logits = piped(*b)
+        if k == 0:
+            assert loss is None and logits is None
+        else:
+            got.append((loss.clone(), logits.clone()))
+    got.append(tuple(t.clone() for t in piped.flush()))
+    assert piped.flush() == (None, None)
+    # the last two batches from the host, H2D under the running step
+    pinned = [tuple(t.pin_memory() for t in b) for b in batches[3:]]
+    for loss, logits in piped.run_host(iter(pinned)):
+        got.append((loss.clone(), logits.clone()))
+    torch.cuda.synchronize()
+    assert len(got) == len(ref) == 5
+    for (l0, g0), (l1, g1) in zip(ref, got):
+        assert torch.equal(l0, l1) and torch.equal(g0, g1)
+    for (name, p), q in zip(det_a.named_parameters(), det_b.parameters()):
+        assert torch.equal(p, q), name
+    plain.close()
+    piped.close()
+
+
 # ------------------------------------------------------------------------- native decoder backward (dfd_decoder_train_*)
 @pytest.mark.parametrize("b,n,k", [(12, 1536, 768), (12, 768, 3072), (3, 256, 256), (33, 3072, 768), (1, 768, 768)])
 @pytest.mark.parametrize("gelu,add", [(False, False), (True, True)])
